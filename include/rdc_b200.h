@@ -1,0 +1,166 @@
+/* rdc_b200.h — C ABI of the B200-native diffusion-curve ray tracer.
+ *
+ * Drop-in boundary for ONE path of MikaZeilstra/RaytracingDiffusionCurves: "XML curve set + rays/pixel ->
+ * float4 image" (ingest -> acceleration structure -> per-frame render -> variable-sigma blur). The
+ * reference has no plugin/FFI interface; its seams are the ones cited below (paths relative to the
+ * reference's optixHello/ directory). Plain pointers and sizes only; every entry point that can fail
+ * returns int (0 = ok, >0 = cudaError_t, <0 = RDC_E_*), never throws, and records a message readable
+ * through rdc_last_error_string(). Entry points that take a stream only enqueue work on it (no hidden
+ * synchronisation) unless their comment says otherwise.
+ */
+#ifndef RDC_B200_H
+#define RDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDC_E_INVALID (-1)  /* bad argument                        */
+#define RDC_E_PARSE (-2)    /* malformed XML / unexpected schema   */
+#define RDC_E_IO (-3)       /* file could not be read / written    */
+#define RDC_E_LIMIT (-4)    /* a structural limit was exceeded     */
+
+typedef void* rdc_stream; /* CUstream / cudaStream_t, as in Params::stream (params.h:45) */
+
+/* ---- ingest: replaces the XML loop of optixHello.cpp:108-117,212-515 and its helpers :1302-1386 ---- */
+
+typedef struct rdc_ingest_options {
+  int use_diffusion_curve_save; /* USE_DIFFUSION_CURVE_SAVE (params.h:24): Orzan-2008 orientation */
+  float default_weight_degree;  /* optixHello.cpp:94  (0.5)  */
+  float endcap_size;            /* optixHello.cpp:96  (8)    */
+} rdc_ingest_options;
+
+/* Read-only view of the structure-of-arrays scene, same arrays (and names) as struct Params
+ * (params.h:60-92). Index arrays hold uint2 {start,count} pairs as two consecutive uint32; vertices and
+ * colours are float3 triples. Every *_u array carries two trailing +INF sentinels beyond n_* so the
+ * reference's over-reading stop walk (DeviceCode.cu:39-43) stays in bounds. */
+typedef struct rdc_scene_arrays {
+  int image_width, image_height; /* curve_set@image_width/@image_height (optixHello.cpp:116-117) */
+  uint32_t n_vertices, n_segments, n_curves;
+  const float* vertices;             /* float3[n_vertices], uniform cubic B-spline control points */
+  const uint32_t* segment_indices;   /* [n_segments] first vertex of each spline segment          */
+  const uint32_t* curve_map;         /* [n_segments] segment -> curve                             */
+  const uint32_t* curve_index;       /* [n_segments] ordinal of the segment inside its curve      */
+  const int32_t* curve_connect;      /* [n_curves]   portal target curve or -1                    */
+  const uint32_t* curve_map_inverse; /* [n_curves]   first segment of each curve                  */
+  uint32_t n_color_left, n_color_right, n_blur, n_weight, n_weight_degree;
+  const uint32_t* color_left_index;  const float* color_left;  const float* color_left_u;
+  const uint32_t* color_right_index; const float* color_right; const float* color_right_u;
+  const uint32_t* blur_index;        const float* blur;        const float* blur_u;
+  const uint32_t* weight_index;      const float* weight;      const float* weight_u;
+  const uint32_t* weight_degree_index; const float* weight_degree; const float* weight_degree_u;
+} rdc_scene_arrays;
+
+typedef struct rdc_host_scene rdc_host_scene; /* opaque, host memory */
+
+void rdc_default_ingest_options(rdc_ingest_options* opts);
+int rdc_ingest_xml_file(const char* path, const rdc_ingest_options* opts, rdc_host_scene** out);
+int rdc_ingest_xml_memory(const char* text, size_t len, const rdc_ingest_options* opts, rdc_host_scene** out);
+int rdc_host_scene_arrays(const rdc_host_scene* scene, rdc_scene_arrays* out);
+void rdc_host_scene_destroy(rdc_host_scene* scene);
+/* canonical text dump of the element tree the loader sees (parser tests) ; caller frees with rdc_free */
+int rdc_xml_dump_file(const char* path, char** out_text);
+void rdc_free(void* p);
+
+/* ---- acceleration structure: replaces optixAccelComputeMemoryUsage/optixAccelBuild over
+ *      OPTIX_PRIMITIVE_TYPE_ROUND_CUBIC_BSPLINE (optixHello.cpp:765-830) and the per-array
+ *      cudaMallocAsync+cudaMemcpyAsync uploads (:524-762) ---- */
+
+typedef struct rdc_accel_options {
+  float curve_width;         /* optixHello.cpp:95 (1e-3): pads chord boxes                          */
+  float flatness_tolerance;  /* max |curve - chord| in XML pixels; chords per segment follow from it */
+  int max_chords_per_segment;
+} rdc_accel_options;
+
+typedef struct rdc_scene rdc_scene; /* opaque: device-resident SoA scene + chords + LBVH, one per device */
+
+typedef struct rdc_scene_info {
+  uint32_t n_segments, n_curves, n_chords, n_nodes, bvh_depth;
+  int has_portals;
+  uint64_t device_bytes;    /* everything the handle owns on the device            */
+  uint64_t traversal_bytes; /* nodes + chord geometry: what a ray touches          */
+  float pad;                /* box padding actually used                           */
+} rdc_scene_info;
+
+void rdc_default_accel_options(rdc_accel_options* opts);
+/* Uploads the arrays and builds chords + Morton LBVH on `stream`. Synchronises the stream once before
+ * returning (the build reads back the chord count), like the reference's set-up phase. */
+int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out);
+int rdc_scene_get_info(const rdc_scene* scene, rdc_scene_info* out);
+/* Test hook: copies the chord list (original order) to host arrays of n_chords entries each.
+ * geom = 4 floats per chord (ax,ay,bx,by); ids = 3 uint32 per chord (segment, k, K). Synchronous. */
+int rdc_scene_download_chords(const rdc_scene* scene, float* geom, uint32_t* ids);
+void rdc_scene_destroy(rdc_scene* scene);
+
+/* ---- per-frame render: replaces optixLaunch(pipeline, stream, d_param, sizeof(Params), &sbt, W, H, 1)
+ *      (optixHello.cpp:1184) running DeviceCode.cu:85-342 ---- */
+
+#define RDC_TRAVERSAL_LBVH 0
+#define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
+
+typedef struct rdc_frame_params {
+  uint32_t image_width, image_height;   /* output size (params.h:48-49)                               */
+  float number_of_rays_per_pixel;       /* a float, as in params.h:55                                 */
+  float zoom_factor, offset_x, offset_y; /* params.h:95-97                                            */
+  uint32_t frame;                       /* params.h:100; part of the Philox key                       */
+  uint32_t seed;                        /* Philox key word 0                                          */
+  uint32_t row_begin, row_end;          /* rows [row_begin,row_end) of the full image to render; the
+                                           image/blur_map pointers address row_begin (band-local)     */
+  int use_diffusion_curve_save;         /* params.h:24                                                */
+  int use_aa;                           /* params.h:28                                                */
+  int max_trace_depth;                  /* params.h:32, 0..31                                         */
+  int traversal;                        /* RDC_TRAVERSAL_*                                            */
+  uint32_t* hit_ids;                    /* optional device array [rows*W*rpp]: chord id of each primary
+                                           ray's first hit, 0xFFFFFFFF for a miss (parity tests)       */
+  float* max_sigma;                     /* optional device float: atomically raised to the largest
+                                           blur_map value written (lets the blur skip all-zero maps)   */
+} rdc_frame_params;
+
+void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t height, float rays_per_pixel);
+/* image = float4[rows*W] (xyz written, w = 1), blur_map = float[rows*W]; both device pointers. */
+int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream);
+
+/* ---- helper kernels: same names and signatures as helperKernels.cu's extern "C" launchers
+ *      (declared at optixHello.cpp:51-54) ---- */
+#ifndef RDC_NO_REFERENCE_HELPER_NAMES
+/* helperKernels.cu:137-148. In-place capable (dest == source). Scratch comes from the stream-ordered
+ * allocator instead of a per-frame cudaMalloc/cudaFree. `image` elements are float4. */
+void gaussianBlur(void* dest, void* source, float* sigma, int width, int height, rdc_stream stream);
+/* helperKernels.cu:43-45 */
+void setFloatDevice(float* dest, unsigned int n, float src, rdc_stream stream);
+/* helperKernels.cu:158-160. The Philox generator is counter-based and keeps no per-pixel state, so this
+ * only validates its arguments; `states` may be NULL. */
+void setupCurand(void* states, int width, int height, rdc_stream stream);
+#endif
+/* Blur with caller-provided scratch (float4[rows_with_halo*W]) on a band of rows, int result. `source`,
+ * `sigma`, `dest` address row 0 of a buffer holding `height` rows; rows [row_begin,row_end) are produced.
+ * max_sigma (optional device float written by rdc_render) lets both passes degrade to a copy when 0. */
+int rdc_gaussian_blur(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
+                      int row_begin, int row_end, const float* max_sigma, rdc_stream stream);
+
+/* ---- whole frame through host memory: the body of the reference's frame loop (optixHello.cpp:1176-1244)
+ *      minus window system: render -> [blur] -> copy to host -> synchronise ---- */
+int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
+                             rdc_stream stream);
+
+/* ---- output conventions of the F11 screenshot (glfw_events.cpp:73-94) ---- */
+/* float4 image -> RGBA8: min(v*255,255), NaN -> 0, rows flipped when flip != 0. Host memory. */
+int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint8_t* out);
+/* binary PPM (P6) writer for headless runs */
+int rdc_write_ppm(const char* path, const uint8_t* rgba, int width, int height);
+
+/* ---- synthetic scenes: n_curves single-segment curves, SplitMix64(seed),
+ *      emitted as XML text in the reference's schema so it passes through the same loader.
+ *      Caller frees *out_text with rdc_free. ---- */
+int rdc_synth_xml(uint32_t n_curves, uint32_t width, uint32_t height, uint64_t seed, char** out_text, size_t* out_len);
+
+const char* rdc_last_error_string(void);
+const char* rdc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDC_B200_H */

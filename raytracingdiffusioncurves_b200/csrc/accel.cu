@@ -1,0 +1,490 @@
+// accel.cu — scene upload + on-GPU acceleration structure.
+//
+// Replaces the reference's per-array uploads (optixHello.cpp:524-762) and the closed
+// optixAccelBuild over round cubic B-spline primitives (optixHello.cpp:765-830):
+//   1. every spline segment is cut into K parameter-uniform chords, K from a flatness bound
+//      (rdc_chord_count), end points evaluated with the bit-exact spline of rdc_math.h;
+//   2. chords are ordered by the 32-bit Morton code of their centre (cub radix sort);
+//   3. a binary radix tree is built over the sorted codes (Karras 2012), boxes are fitted bottom-up with
+//      one atomic counter per inner node, each node ends up holding both children's padded boxes.
+// The chord's ORIGINAL id (segment order, then k) is what hit parity is defined on; Morton order is only
+// a memory layout.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "device_scene.h"
+#include "rdc_math.h"
+
+namespace rdc {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_error; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+struct Bounds {
+  float xmin, ymin, xmax, ymax;
+};
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ void load_segment(const float2* vertices, uint32_t first, rdc_f2 v[4]) {
+  const float4* p = reinterpret_cast<const float4*>(vertices + first);  // first % 4 == 0 -> 32-byte aligned
+  float4 a = __ldg(p), b = __ldg(p + 1);
+  v[0] = {a.x, a.y};
+  v[1] = {a.z, a.w};
+  v[2] = {b.x, b.y};
+  v[3] = {b.z, b.w};
+}
+
+__global__ void k_chord_counts(const float2* vertices, const uint32_t* segment_indices, uint32_t n_segments, float tol,
+                               int kmax, uint32_t* counts) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segments) return;
+  rdc_f2 v[4];
+  load_segment(vertices, segment_indices[s], v);
+  counts[s] = (uint32_t)rdc_chord_count(v[0], v[1], v[2], v[3], tol, kmax);
+}
+
+__global__ void k_emit_chords(const float2* vertices, const uint32_t* segment_indices, const uint32_t* base,
+                              uint32_t n_segments, uint32_t n_chords, float4* geom, uint4* ids, Bounds* bounds) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chords) return;
+  // segment = last s with base[s] <= c
+  uint32_t lo = 0, hi = n_segments;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (base[mid] <= c) lo = mid; else hi = mid;
+  }
+  uint32_t seg = lo;
+  int k = (int)(c - base[seg]);
+  int K = (int)(base[seg + 1] - base[seg]);
+  rdc_f2 v[4];
+  load_segment(vertices, segment_indices[seg], v);
+  rdc_f2 a = rdc_spline_point(rdc_chord_u(k, K), v[0], v[1], v[2], v[3]);
+  rdc_f2 b = rdc_spline_point(rdc_chord_u(k + 1, K), v[0], v[1], v[2], v[3]);
+  geom[c] = make_float4(a.x, a.y, b.x, b.y);
+  ids[c] = make_uint4(c, seg, (uint32_t)k, (uint32_t)K);
+  atomic_min_float(&bounds->xmin, fminf(a.x, b.x));
+  atomic_min_float(&bounds->ymin, fminf(a.y, b.y));
+  atomic_max_float(&bounds->xmax, fmaxf(a.x, b.x));
+  atomic_max_float(&bounds->ymax, fmaxf(a.y, b.y));
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+__global__ void k_morton(const float4* geom, uint32_t n, Bounds b, uint32_t* codes, uint32_t* order) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float4 g = geom[c];
+  float cx = 0.5f * (g.x + g.z), cy = 0.5f * (g.y + g.w);
+  float ex = fmaxf(b.xmax - b.xmin, 1e-20f), ey = fmaxf(b.ymax - b.ymin, 1e-20f);
+  float nx = fminf(fmaxf((cx - b.xmin) / ex, 0.0f), 1.0f);
+  float ny = fminf(fmaxf((cy - b.ymin) / ey, 0.0f), 1.0f);
+  uint32_t qx = (uint32_t)(nx * 65535.0f), qy = (uint32_t)(ny * 65535.0f);
+  codes[c] = spread16(qx) | (spread16(qy) << 1);
+  order[c] = c;
+}
+
+__global__ void k_gather(const uint32_t* order, const float4* geom_in, const uint4* ids_in, uint32_t n, float4* geom,
+                         uint4* ids) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t src = order[i];
+  geom[i] = geom_in[src];
+  ids[i] = ids_in[src];
+}
+
+// length of the common prefix of the (code, position) keys i and j; -1 outside the array
+__device__ __forceinline__ int prefix_len(const uint32_t* codes, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint32_t a = codes[i], b = codes[j];
+  if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clz(a ^ b);
+}
+
+__global__ void k_radix_tree(const uint32_t* codes, int n, BvhNode* nodes, int* leaf_parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (prefix_len(codes, n, i, i + 1) - prefix_len(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = prefix_len(codes, n, i, i - d);
+  int lmax = 2;
+  while (prefix_len(codes, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (prefix_len(codes, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = prefix_len(codes, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (prefix_len(codes, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  int left = (lo == gamma) ? ~gamma : gamma;
+  int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  nodes[i].left = left;
+  nodes[i].right = right;
+  nodes[i].pad = 0;
+  if (i == 0) nodes[i].parent = -1;
+  if (left < 0) leaf_parent[gamma] = i; else nodes[left].parent = i;
+  if (right < 0) leaf_parent[gamma + 1] = i; else nodes[right].parent = i;
+}
+
+__device__ __forceinline__ float4 chord_box(float4 g, float pad) {
+  return make_float4(fminf(g.x, g.z) - pad, fminf(g.y, g.w) - pad, fmaxf(g.x, g.z) + pad, fmaxf(g.y, g.w) + pad);
+}
+__device__ __forceinline__ float4 box_union(float4 a, float4 b) {
+  return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// Bottom-up fit. The second thread to reach a node owns it: both children are complete by then.
+__global__ void k_fit_boxes(const float4* geom, int n, float pad, const int* leaf_parent, BvhNode* nodes,
+                            float4* node_box, unsigned int* arrivals) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n) return;
+  int node = leaf_parent[leaf];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&arrivals[node], 1u) == 0u) return;
+    __threadfence();
+    int l = nodes[node].left, r = nodes[node].right;
+    float4 lb = l < 0 ? chord_box(geom[~l], pad) : __ldcg(&node_box[l]);  // L2: written by another SM
+    float4 rb = r < 0 ? chord_box(geom[~r], pad) : __ldcg(&node_box[r]);
+    nodes[node].lbox = lb;
+    nodes[node].rbox = rb;
+    node_box[node] = box_union(lb, rb);
+    node = nodes[node].parent;
+  }
+}
+
+__global__ void k_single_chord_root(const float4* geom, float pad, BvhNode* nodes) {
+  const float inf = __int_as_float(0x7f800000);
+  nodes[0].lbox = chord_box(geom[0], pad);
+  nodes[0].rbox = make_float4(inf, inf, -inf, -inf);  // never entered
+  nodes[0].left = ~0;
+  nodes[0].right = ~0;
+  nodes[0].parent = -1;
+  nodes[0].pad = 0;
+}
+
+__global__ void k_depth(const int* leaf_parent, const BvhNode* nodes, int n, unsigned int* max_depth) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n) return;
+  unsigned int depth = 0;
+  for (int node = leaf_parent[leaf]; node >= 0; node = nodes[node].parent) ++depth;
+  atomicMax(max_depth, depth);
+}
+
+__global__ void k_fill(float* dest, unsigned int n, float v) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += blockDim.x * gridDim.x) dest[i] = v;
+}
+
+struct Uploader {
+  rdc_scene* s;
+  cudaStream_t stream;
+  int status = 0;
+
+  template <class T>
+  T* alloc(size_t count) {
+    if (status) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+      status = cuda_fail(e, "cudaMalloc");
+      return nullptr;
+    }
+    s->allocations.push_back(p);
+    s->info.device_bytes += (count ? count : 1) * sizeof(T);
+    return static_cast<T*>(p);
+  }
+  template <class T>
+  T* upload(const T* host, size_t count) {
+    T* d = alloc<T>(count);
+    if (status || !count) return d;
+    cudaError_t e = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) status = cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    return d;
+  }
+};
+
+}  // namespace
+
+int set_float(float* dest, unsigned n, float v, cudaStream_t stream) {
+  if (n == 0) return 0;
+  unsigned grid = blocks_for(n);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  k_fill<<<grid, kThreads, 0, stream>>>(dest, n, v);
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void destroy_scene(rdc_scene* s) {
+  if (!s) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(s->device);
+  for (void* p : s->allocations) cudaFree(p);
+  cudaSetDevice(prev);
+  delete s;
+}
+
+int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStream_t stream, rdc_scene** out) {
+  if (a.n_segments == 0 || a.n_curves == 0 || a.n_vertices < 4) {
+    set_error("accel: empty scene");
+    return RDC_E_INVALID;
+  }
+  if (!(o.flatness_tolerance > 0.0f) || o.max_chords_per_segment < 1 || !(o.curve_width >= 0.0f)) {
+    set_error("accel: bad options");
+    return RDC_E_INVALID;
+  }
+  for (uint32_t i = 0; i < a.n_segments; ++i)
+    if (a.segment_indices[i] % 4 != 0 || a.segment_indices[i] + 4 > a.n_vertices) {
+      set_error("accel: segment %u does not address four aligned control points", i);
+      return RDC_E_INVALID;
+    }
+  rdc_scene* s = new rdc_scene();
+  cudaGetDevice(&s->device);
+  Uploader up{s, stream};
+  DevScene& d = s->dev;
+  bool portals = false;
+  for (uint32_t c = 0; c < a.n_curves; ++c) portals |= a.curve_connect[c] >= 0;
+
+  // ---- scene arrays ------------------------------------------------------------------------------
+  {
+    std::vector<float2> v2(a.n_vertices);
+    for (uint32_t i = 0; i < a.n_vertices; ++i) v2[i] = make_float2(a.vertices[3 * i], a.vertices[3 * i + 1]);
+    d.vertices = up.upload(v2.data(), v2.size());
+  }
+  d.segment_indices = up.upload(a.segment_indices, a.n_segments);
+  d.curve_map = up.upload(a.curve_map, a.n_segments);
+  d.curve_index = up.upload(a.curve_index, a.n_segments);
+  d.curve_connect = up.upload(a.curve_connect, a.n_curves);
+  d.curve_map_inverse = up.upload(a.curve_map_inverse, a.n_curves);
+  const size_t colour_len = (size_t)(a.n_color_left > a.n_color_right ? a.n_color_left : a.n_color_right) + 2;
+  auto colours = [&](const uint32_t* index, const float* rgb, const float* u) {
+    DevStops st{};
+    st.index = reinterpret_cast<const uint2*>(up.upload(index, (size_t)2 * a.n_curves));
+    st.u = up.upload(u, colour_len);
+    std::vector<float4> c4(colour_len);
+    for (size_t i = 0; i < colour_len; ++i) c4[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
+    st.rgb = up.upload(c4.data(), c4.size());
+    return st;
+  };
+  auto scalars = [&](const uint32_t* index, const float* value, const float* u, uint32_t n) {
+    DevStops st{};
+    st.index = reinterpret_cast<const uint2*>(up.upload(index, (size_t)2 * a.n_curves));
+    st.u = up.upload(u, (size_t)n + 2);
+    st.value = up.upload(value, (size_t)n + 2);
+    return st;
+  };
+  d.color_left = colours(a.color_left_index, a.color_left, a.color_left_u);
+  d.color_right = colours(a.color_right_index, a.color_right, a.color_right_u);
+  d.blur = scalars(a.blur_index, a.blur, a.blur_u, a.n_blur);
+  d.weight = scalars(a.weight_index, a.weight, a.weight_u, a.n_weight);
+  d.weight_degree = scalars(a.weight_degree_index, a.weight_degree, a.weight_degree_u, a.n_weight_degree);
+  d.n_segments = a.n_segments;
+  d.n_curves = a.n_curves;
+
+  // ---- chords ------------------------------------------------------------------------------------
+  const uint32_t nseg = a.n_segments;
+  uint32_t* counts = up.alloc<uint32_t>(nseg + 1);
+  uint32_t* base = up.alloc<uint32_t>(nseg + 1);
+  Bounds* bounds = up.alloc<Bounds>(1);
+  s->zero_sigma = up.alloc<float>(1);
+  auto fail = [&](int code) {
+    destroy_scene(s);
+    return code;
+  };
+  if (up.status) return fail(up.status);
+#define BUILD_CUDA(call)                                              \
+  do {                                                                \
+    cudaError_t e__ = (call);                                         \
+    if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call));       \
+  } while (0)
+  BUILD_CUDA(cudaMemsetAsync(counts, 0, (nseg + 1) * sizeof(uint32_t), stream));
+  BUILD_CUDA(cudaMemsetAsync(s->zero_sigma, 0, sizeof(float), stream));
+  k_chord_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(d.vertices, d.segment_indices, nseg, o.flatness_tolerance,
+                                                            o.max_chords_per_segment, counts);
+  BUILD_CUDA(cudaGetLastError());
+  size_t temp_bytes = 0;
+  BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, base, (int)(nseg + 1), stream));
+  void* scan_temp = nullptr;
+  BUILD_CUDA(cudaMalloc(&scan_temp, temp_bytes ? temp_bytes : 1));
+  cudaError_t scan_err = cub::DeviceScan::ExclusiveSum(scan_temp, temp_bytes, counts, base, (int)(nseg + 1), stream);
+  uint32_t n_chords = 0;
+  if (scan_err == cudaSuccess)
+    scan_err = cudaMemcpyAsync(&n_chords, base + nseg, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+  if (scan_err == cudaSuccess) scan_err = cudaStreamSynchronize(stream);
+  cudaFree(scan_temp);
+  BUILD_CUDA(scan_err);
+  if (n_chords == 0 || n_chords > (1u << 30)) {
+    set_error("accel: %u chords", n_chords);
+    return fail(RDC_E_LIMIT);
+  }
+
+  float4* geom_in = nullptr;
+  uint4* ids_in = nullptr;
+  uint32_t *codes_in = nullptr, *codes = nullptr, *order_in = nullptr, *order = nullptr;
+  void* sort_temp = nullptr;
+  float4* node_box = nullptr;
+  unsigned int* arrivals = nullptr;
+  int* leaf_parent = nullptr;
+  auto free_temps = [&]() {
+    cudaFree(geom_in); cudaFree(ids_in); cudaFree(codes_in); cudaFree(codes); cudaFree(order_in); cudaFree(order);
+    cudaFree(sort_temp); cudaFree(node_box); cudaFree(arrivals); cudaFree(leaf_parent);
+  };
+#define TEMP_CUDA(call)                                         \
+  do {                                                          \
+    cudaError_t e__ = (call);                                   \
+    if (e__ != cudaSuccess) {                                   \
+      free_temps();                                             \
+      return fail(cuda_fail(e__, #call));                       \
+    }                                                           \
+  } while (0)
+  const uint32_t n_nodes = n_chords > 1 ? n_chords - 1 : 1;
+  TEMP_CUDA(cudaMalloc(&geom_in, n_chords * sizeof(float4)));
+  TEMP_CUDA(cudaMalloc(&ids_in, n_chords * sizeof(uint4)));
+  TEMP_CUDA(cudaMalloc(&codes_in, n_chords * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&codes, n_chords * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&order_in, n_chords * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&order, n_chords * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&node_box, n_nodes * sizeof(float4)));
+  TEMP_CUDA(cudaMalloc(&arrivals, n_nodes * sizeof(unsigned int)));
+  TEMP_CUDA(cudaMalloc(&leaf_parent, n_chords * sizeof(int)));
+  float4* geom = up.alloc<float4>(n_chords);
+  uint4* ids = up.alloc<uint4>(n_chords);
+  BvhNode* nodes = up.alloc<BvhNode>(n_nodes);
+  unsigned int* max_depth = up.alloc<unsigned int>(1);
+  if (up.status) {
+    free_temps();
+    return fail(up.status);
+  }
+
+  const float inf = std::numeric_limits<float>::infinity();
+  Bounds init{inf, inf, -inf, -inf};
+  TEMP_CUDA(cudaMemcpyAsync(bounds, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+  k_emit_chords<<<blocks_for(n_chords), kThreads, 0, stream>>>(d.vertices, d.segment_indices, base, nseg, n_chords,
+                                                               geom_in, ids_in, bounds);
+  TEMP_CUDA(cudaGetLastError());
+  Bounds hb{};
+  TEMP_CUDA(cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, stream));
+  TEMP_CUDA(cudaStreamSynchronize(stream));
+  if (!(std::isfinite(hb.xmin) && std::isfinite(hb.ymin) && std::isfinite(hb.xmax) && std::isfinite(hb.ymax))) {
+    free_temps();
+    set_error("accel: control points are not finite");
+    return fail(RDC_E_INVALID);
+  }
+  float extent = std::fmax(std::fmax(std::fabs(hb.xmin), std::fabs(hb.xmax)), std::fmax(std::fabs(hb.ymin), std::fabs(hb.ymax)));
+  // curve_width thickens every chord's box; the relative term keeps the padding above the rounding of
+  // the chord test (a few ulp of the largest coordinate), which is what makes culling exact.
+  const float pad = o.curve_width + 4e-6f * extent;
+
+  k_morton<<<blocks_for(n_chords), kThreads, 0, stream>>>(geom_in, n_chords, hb, codes_in, order_in);
+  TEMP_CUDA(cudaGetLastError());
+  size_t sort_bytes = 0;
+  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, codes_in, codes, order_in, order, (int)n_chords, 0, 32, stream));
+  TEMP_CUDA(cudaMalloc(&sort_temp, sort_bytes ? sort_bytes : 1));
+  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, sort_bytes, codes_in, codes, order_in, order, (int)n_chords, 0, 32, stream));
+  k_gather<<<blocks_for(n_chords), kThreads, 0, stream>>>(order, geom_in, ids_in, n_chords, geom, ids);
+  TEMP_CUDA(cudaGetLastError());
+
+  TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
+  if (n_chords == 1) {
+    k_single_chord_root<<<1, 1, 0, stream>>>(geom, pad, nodes);
+    TEMP_CUDA(cudaGetLastError());
+  } else {
+    TEMP_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
+    k_radix_tree<<<blocks_for(n_chords - 1), kThreads, 0, stream>>>(codes, (int)n_chords, nodes, leaf_parent);
+    TEMP_CUDA(cudaGetLastError());
+    k_fit_boxes<<<blocks_for(n_chords), kThreads, 0, stream>>>(geom, (int)n_chords, pad, leaf_parent, nodes, node_box, arrivals);
+    TEMP_CUDA(cudaGetLastError());
+    k_depth<<<blocks_for(n_chords), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_chords, max_depth);
+    TEMP_CUDA(cudaGetLastError());
+  }
+  unsigned int depth = 0;
+  TEMP_CUDA(cudaMemcpyAsync(&depth, max_depth, sizeof depth, cudaMemcpyDeviceToHost, stream));
+  TEMP_CUDA(cudaStreamSynchronize(stream));
+  free_temps();
+  if (depth > 62) {
+    set_error("accel: tree depth %u exceeds the traversal stack", depth);
+    return fail(RDC_E_LIMIT);
+  }
+
+  d.chord_geom = geom;
+  d.chord_ids = ids;
+  d.seg_chord_base = base;
+  d.seg_chord_count = counts;
+  d.nodes = nodes;
+  d.n_chords = n_chords;
+  d.n_nodes = n_nodes;
+  s->info.n_segments = a.n_segments;
+  s->info.n_curves = a.n_curves;
+  s->info.n_chords = n_chords;
+  s->info.n_nodes = n_nodes;
+  s->info.bvh_depth = depth ? depth : 1;
+  s->info.has_portals = portals ? 1 : 0;
+  s->info.traversal_bytes = (uint64_t)n_nodes * sizeof(BvhNode) + (uint64_t)n_chords * sizeof(float4);
+  s->info.pad = pad;
+  *out = s;
+  return 0;
+#undef BUILD_CUDA
+#undef TEMP_CUDA
+}
+
+int download_chords(const rdc_scene* s, float* geom, uint32_t* ids) {
+  const uint32_t n = s->dev.n_chords;
+  std::vector<float4> g(n);
+  std::vector<uint4> id(n);
+  RDC_CUDA(cudaMemcpy(g.data(), s->dev.chord_geom, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  RDC_CUDA(cudaMemcpy(id.data(), s->dev.chord_ids, n * sizeof(uint4), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t c = id[i].x;
+    if (c >= n) {
+      set_error("chord table is corrupt");
+      return RDC_E_INVALID;
+    }
+    geom[4 * c + 0] = g[i].x; geom[4 * c + 1] = g[i].y; geom[4 * c + 2] = g[i].z; geom[4 * c + 3] = g[i].w;
+    ids[3 * c + 0] = id[i].y; ids[3 * c + 1] = id[i].z; ids[3 * c + 2] = id[i].w;
+  }
+  return 0;
+}
+
+}  // namespace rdc

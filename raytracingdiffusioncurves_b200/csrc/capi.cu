@@ -1,0 +1,314 @@
+// capi.cu — the extern "C" surface declared in include/rdc_b200.h. No C++ exception crosses it.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+
+#include "device_scene.h"
+#include "host_scene.h"
+#include "xml_dom.h"
+
+namespace rdc {
+const char* last_error();
+}
+
+namespace {
+
+template <class F>
+int guarded(int parse_code, F&& body) {
+  try {
+    return body();
+  } catch (const rdc::XmlError& e) {
+    rdc::set_error("%s", e.what());
+    return RDC_E_PARSE;
+  } catch (const std::bad_alloc&) {
+    rdc::set_error("out of host memory");
+    return RDC_E_LIMIT;
+  } catch (const std::exception& e) {
+    rdc::set_error("%s", e.what());
+    return parse_code;
+  } catch (...) {
+    rdc::set_error("unknown failure");
+    return RDC_E_INVALID;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rdc_last_error_string(void) { return rdc::last_error(); }
+const char* rdc_version(void) { return "rdc_b200 0.1 (sm_100a)"; }
+void rdc_free(void* p) { std::free(p); }
+
+void rdc_default_ingest_options(rdc_ingest_options* o) {
+  if (!o) return;
+  o->use_diffusion_curve_save = 1;  // params.h:24
+  o->default_weight_degree = 0.5f;  // optixHello.cpp:94
+  o->endcap_size = 8.0f;            // optixHello.cpp:96
+}
+
+int rdc_ingest_xml_file(const char* path, const rdc_ingest_options* opts, rdc_host_scene** out) {
+  if (!path || !out) {
+    rdc::set_error("ingest: null argument");
+    return RDC_E_INVALID;
+  }
+  rdc_ingest_options o;
+  rdc_default_ingest_options(&o);
+  if (opts) o = *opts;
+  return guarded(RDC_E_PARSE, [&]() {
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) {
+      rdc::set_error("ingest: cannot open %s", path);
+      return RDC_E_IO;
+    }
+    std::fclose(f);
+    auto* s = new rdc_host_scene();
+    try {
+      rdc::ingest_xml_file(path, o, *s);
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    *out = s;
+    return 0;
+  });
+}
+
+int rdc_ingest_xml_memory(const char* text, size_t len, const rdc_ingest_options* opts, rdc_host_scene** out) {
+  if (!text || !out) {
+    rdc::set_error("ingest: null argument");
+    return RDC_E_INVALID;
+  }
+  rdc_ingest_options o;
+  rdc_default_ingest_options(&o);
+  if (opts) o = *opts;
+  return guarded(RDC_E_PARSE, [&]() {
+    auto* s = new rdc_host_scene();
+    try {
+      rdc::ingest_xml_text(text, len, o, *s);
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    *out = s;
+    return 0;
+  });
+}
+
+int rdc_host_scene_arrays(const rdc_host_scene* scene, rdc_scene_arrays* out) {
+  if (!scene || !out) {
+    rdc::set_error("scene arrays: null argument");
+    return RDC_E_INVALID;
+  }
+  scene->view(out);
+  return 0;
+}
+
+void rdc_host_scene_destroy(rdc_host_scene* scene) { delete scene; }
+
+int rdc_xml_dump_file(const char* path, char** out_text) {
+  if (!path || !out_text) {
+    rdc::set_error("xml dump: null argument");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_PARSE, [&]() {
+    auto root = rdc::xml_parse_file(path);
+    std::string s;
+    rdc::xml_dump(*root, 0, s);
+    char* buf = (char*)std::malloc(s.size() + 1);
+    if (!buf) throw std::bad_alloc();
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    *out_text = buf;
+    return 0;
+  });
+}
+
+void rdc_default_accel_options(rdc_accel_options* o) {
+  if (!o) return;
+  o->curve_width = 1e-3f;  // optixHello.cpp:95
+  o->flatness_tolerance = 0.05f;
+  o->max_chords_per_segment = 1024;
+}
+
+int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out) {
+  if (!arrays || !out) {
+    rdc::set_error("accel: null argument");
+    return RDC_E_INVALID;
+  }
+  rdc_accel_options o;
+  rdc_default_accel_options(&o);
+  if (opts) o = *opts;
+  return guarded(RDC_E_INVALID, [&]() { return rdc::build_scene(*arrays, o, (cudaStream_t)stream, out); });
+}
+
+int rdc_scene_get_info(const rdc_scene* scene, rdc_scene_info* out) {
+  if (!scene || !out) {
+    rdc::set_error("scene info: null argument");
+    return RDC_E_INVALID;
+  }
+  *out = scene->info;
+  return 0;
+}
+
+int rdc_scene_download_chords(const rdc_scene* scene, float* geom, uint32_t* ids) {
+  if (!scene || !geom || !ids) {
+    rdc::set_error("download chords: null argument");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_INVALID, [&]() { return rdc::download_chords(scene, geom, ids); });
+}
+
+void rdc_scene_destroy(rdc_scene* scene) { rdc::destroy_scene(scene); }
+
+void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t height, float rays_per_pixel) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->image_width = width;
+  p->image_height = height;
+  p->number_of_rays_per_pixel = rays_per_pixel;
+  p->zoom_factor = 1.0f;  // optixHello.cpp:89-91
+  p->offset_x = 0.0f;
+  p->offset_y = 0.0f;
+  p->frame = 0;
+  p->seed = 0;
+  p->row_begin = 0;
+  p->row_end = height;
+  p->use_diffusion_curve_save = 1;  // params.h:24
+  p->use_aa = 1;                    // params.h:28
+  p->max_trace_depth = 2;           // params.h:32
+  p->traversal = RDC_TRAVERSAL_LBVH;
+  p->hit_ids = nullptr;
+  p->max_sigma = nullptr;
+}
+
+int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream) {
+  if (!scene || !params) {
+    rdc::set_error("render: null argument");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_INVALID, [&]() {
+    return rdc::render(scene, *params, reinterpret_cast<float4*>(image), blur_map, (cudaStream_t)stream);
+  });
+}
+
+int rdc_gaussian_blur(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
+                      int row_begin, int row_end, const float* max_sigma, rdc_stream stream) {
+  return rdc::gaussian_blur(static_cast<float4*>(dest), static_cast<const float4*>(source), sigma,
+                            static_cast<float4*>(scratch), width, height, row_begin, row_end, max_sigma,
+                            (cudaStream_t)stream);
+}
+
+// Reference-named helpers. They return void like the originals; failures are readable through
+// rdc_last_error_string() and, being CUDA errors, through cudaGetLastError().
+void gaussianBlur(void* dest, void* source, float* sigma, int width, int height, rdc_stream stream) {
+  if (width <= 0 || height <= 0) {
+    rdc::set_error("gaussianBlur: bad size");
+    return;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  void* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync(&scratch, sizeof(float4) * (size_t)width * height, st);
+  if (e != cudaSuccess) {
+    rdc::cuda_fail(e, "cudaMallocAsync(blur scratch)");
+    return;
+  }
+  rdc::gaussian_blur(static_cast<float4*>(dest), static_cast<const float4*>(source), sigma, static_cast<float4*>(scratch),
+                     width, height, 0, height, nullptr, st);
+  e = cudaFreeAsync(scratch, st);
+  if (e != cudaSuccess) rdc::cuda_fail(e, "cudaFreeAsync(blur scratch)");
+}
+
+void setFloatDevice(float* dest, unsigned int n, float src, rdc_stream stream) {
+  rdc::set_float(dest, n, src, (cudaStream_t)stream);
+}
+
+void setupCurand(void* states, int width, int height, rdc_stream stream) {
+  (void)states;
+  (void)stream;
+  if (width <= 0 || height <= 0) rdc::set_error("setupCurand: bad size");
+}
+
+int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
+                             rdc_stream stream) {
+  if (!scene || !params || !host_image) {
+    rdc::set_error("render frame: null argument");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_INVALID, [&]() {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (params->row_begin >= params->row_end || params->row_end > params->image_height) {
+      rdc::set_error("render frame: bad row band");
+      return RDC_E_INVALID;
+    }
+    const size_t rows = params->row_end - params->row_begin;
+    const size_t n = rows * params->image_width;
+    float4 *image = nullptr, *scratch = nullptr;
+    float* sigma = nullptr;
+    float* flag = nullptr;
+    RDC_CUDA(cudaMallocAsync((void**)&image, n * sizeof(float4), st));
+    RDC_CUDA(cudaMallocAsync((void**)&sigma, n * sizeof(float) + sizeof(float), st));
+    rdc_frame_params p = *params;
+    if (use_blur) {
+      RDC_CUDA(cudaMallocAsync((void**)&scratch, n * sizeof(float4), st));
+      flag = sigma + n;
+      RDC_CUDA(cudaMemsetAsync(flag, 0, sizeof(float), st));
+      p.max_sigma = flag;
+    }
+    int rc = rdc::render(scene, p, image, sigma, st);
+    if (rc == 0 && use_blur)
+      rc = rdc::gaussian_blur(image, image, sigma, scratch, (int)params->image_width, (int)rows, 0, (int)rows, flag, st);
+    if (rc == 0) {
+      cudaError_t e = cudaMemcpyAsync(host_image, image, n * sizeof(float4), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) rc = rdc::cuda_fail(e, "cudaMemcpyAsync(D2H image)");
+    }
+    cudaFreeAsync(image, st);
+    cudaFreeAsync(sigma, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e != cudaSuccess) rc = rdc::cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+  });
+}
+
+int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint8_t* out) {
+  if (!image || !out || width <= 0 || height <= 0) {
+    rdc::set_error("image_to_rgba8: bad argument");
+    return RDC_E_INVALID;
+  }
+  // glfw_events.cpp:73-94: min(v*255, 255) stored to an unsigned char, rows flipped for Orzan saves.
+  for (int y = 0; y < height; ++y) {
+    const float* src = image + (size_t)4 * width * y;
+    uint8_t* dst = out + (size_t)4 * width * (flip ? height - 1 - y : y);
+    for (int i = 0; i < 4 * width; ++i) {
+      float v = std::fmin(src[i] * 255, 255.0f);
+      dst[i] = (v == v && v > 0.0f) ? (uint8_t)v : 0;  // NaN (all rays missed) and negatives -> 0
+    }
+  }
+  return 0;
+}
+
+int rdc_write_ppm(const char* path, const uint8_t* rgba, int width, int height) {
+  if (!path || !rgba || width <= 0 || height <= 0) {
+    rdc::set_error("write_ppm: bad argument");
+    return RDC_E_INVALID;
+  }
+  std::FILE* f = std::fopen(path, "wb");
+  if (!f) {
+    rdc::set_error("write_ppm: cannot open %s", path);
+    return RDC_E_IO;
+  }
+  std::fprintf(f, "P6\n%d %d\n255\n", width, height);
+  for (size_t i = 0; i < (size_t)width * height; ++i) std::fwrite(rgba + 4 * i, 1, 3, f);
+  bool ok = std::fclose(f) == 0;
+  if (!ok) {
+    rdc::set_error("write_ppm: write failed for %s", path);
+    return RDC_E_IO;
+  }
+  return 0;
+}
+
+}  // extern "C"

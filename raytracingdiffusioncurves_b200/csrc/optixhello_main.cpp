@@ -1,0 +1,171 @@
+// OptixHello <xml> <rays_per_pixel> [options] — headless stand-in for the reference executable.
+//
+// Keeps the reference's command line (optixHello.cpp:81-102): two positional arguments, the same usage
+// message and exit code 1 when they are missing, the xml path taken relative to the current directory,
+// rays per pixel through atoi; and its two timing lines ("Setup took : N ms", :1157;
+// "Average frame time  : X ms", :1263). There is no window: the frame loop (:1163-1259) runs --frames
+// times and the last frame is written to --out. Everything after the positionals is new surface
+// (SURVEY.md Appendix E).
+#include <cuda_runtime.h>
+
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/params.h"
+#include "../../include/rdc_b200.h"
+
+#define CALL_CHECK(call)                                                                                       \
+  do {                                                                                                         \
+    int rc__ = (call);                                                                                         \
+    if (rc__ != 0) {                                                                                           \
+      std::cerr << "call (" << #call << ") failed with code " << rc__ << " (line " << __LINE__ << " in " << __FILE__ \
+                << "): " << rdc_last_error_string() << std::endl;                                            \
+      return 2;                                                                                                \
+    }                                                                                                          \
+  } while (0)
+
+static void usage_options() {
+  std::cout << "options: --width W --height H --frames N --out file.ppm --zoom Z --offset-x X --offset-y Y\n"
+               "         --seed S --max-depth D --tolerance T --curve-width R --endcap-size E --weight-degree G\n"
+               "         --native (not an Orzan save) --no-blur --no-aa --denoiser (ignored) --brute-force --device I\n";
+}
+
+int main(int argc, char* argv[]) {
+  if (argc < 3) {
+    std::cout << "Please provide a path to a diffusion curve xml and the number of rays per pixel" << std::endl;
+    return 1;
+  }
+  const int number_of_rays = std::atoi(argv[2]);
+  std::string file_name = argv[1];
+  if (file_name.empty() || file_name[0] != '/') {
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) return 2;
+    file_name = std::string(cwd) + "/" + file_name;
+  }
+
+  rdc_ingest_options ingest;
+  rdc_default_ingest_options(&ingest);
+  ingest.use_diffusion_curve_save = USE_DIFFUSION_CURVE_SAVE;
+  ingest.default_weight_degree = RDC_DEFAULT_WEIGHT_DEGREE;
+  ingest.endcap_size = RDC_DEFAULT_ENDCAP_SIZE;
+  rdc_accel_options accel;
+  rdc_default_accel_options(&accel);
+  accel.curve_width = RDC_DEFAULT_CURVE_WIDTH;
+  bool use_blur = USE_BLUR, use_aa = USE_AA, brute = false;
+  int max_depth = MAX_TRACE_DEPTH, frames = 1, device = 0;
+  int out_w = 0, out_h = 0;
+  float zoom = -1.0f, off_x = RDC_DEFAULT_OFFSET_X, off_y = RDC_DEFAULT_OFFSET_Y;
+  unsigned seed = 0;
+  std::string out_path;
+  for (int i = 3; i < argc; ++i) {
+    std::string a = argv[i];
+    auto value = [&]() -> const char* {
+      if (i + 1 >= argc) {
+        std::cerr << "missing value for " << a << std::endl;
+        std::exit(1);
+      }
+      return argv[++i];
+    };
+    if (a == "--width") out_w = std::atoi(value());
+    else if (a == "--height") out_h = std::atoi(value());
+    else if (a == "--frames") frames = std::atoi(value());
+    else if (a == "--out") out_path = value();
+    else if (a == "--zoom") zoom = (float)std::atof(value());
+    else if (a == "--offset-x") off_x = (float)std::atof(value());
+    else if (a == "--offset-y") off_y = (float)std::atof(value());
+    else if (a == "--seed") seed = (unsigned)std::strtoul(value(), nullptr, 0);
+    else if (a == "--max-depth") max_depth = std::atoi(value());
+    else if (a == "--tolerance") accel.flatness_tolerance = (float)std::atof(value());
+    else if (a == "--curve-width") accel.curve_width = (float)std::atof(value());
+    else if (a == "--endcap-size") ingest.endcap_size = (float)std::atof(value());
+    else if (a == "--weight-degree") ingest.default_weight_degree = (float)std::atof(value());
+    else if (a == "--native") ingest.use_diffusion_curve_save = 0;
+    else if (a == "--no-blur") use_blur = false;
+    else if (a == "--no-aa") use_aa = false;
+    else if (a == "--denoiser") {}  // USE_DENOISER: accepted, ignored (closed OptiX model)
+    else if (a == "--brute-force") brute = true;
+    else if (a == "--device") device = std::atoi(value());
+    else if (a == "--help") { usage_options(); return 0; }
+    else {
+      std::cerr << "unknown option " << a << std::endl;
+      usage_options();
+      return 1;
+    }
+  }
+  if (frames < 1) frames = 1;
+
+  auto start_time = std::chrono::high_resolution_clock::now();
+  if (cudaSetDevice(device) != cudaSuccess) {
+    std::cerr << "no usable CUDA device " << device << " (this program has no CPU path)" << std::endl;
+    return 2;
+  }
+  cudaStream_t stream;
+  CALL_CHECK((int)cudaStreamCreate(&stream));
+  rdc_host_scene* host = nullptr;
+  CALL_CHECK(rdc_ingest_xml_file(file_name.c_str(), &ingest, &host));
+  rdc_scene_arrays arrays;
+  CALL_CHECK(rdc_host_scene_arrays(host, &arrays));
+  rdc_scene* scene = nullptr;
+  CALL_CHECK(rdc_accel_build(&arrays, &accel, stream, &scene));
+  rdc_scene_info info;
+  CALL_CHECK(rdc_scene_get_info(scene, &info));
+
+  // resolution comes from the XML unless overridden; the default zoom keeps the XML frame visible
+  const int width = out_w > 0 ? out_w : arrays.image_width;
+  const int height = out_h > 0 ? out_h : arrays.image_height;
+  if (zoom <= 0.0f) zoom = (out_h > 0 && out_h != arrays.image_height) ? (float)arrays.image_height / (float)height : RDC_DEFAULT_ZOOM_FACTOR;
+
+  rdc_frame_params params;
+  rdc_default_frame_params(&params, (uint32_t)width, (uint32_t)height, (float)number_of_rays);
+  params.zoom_factor = zoom;
+  params.offset_x = off_x;
+  params.offset_y = off_y;
+  params.seed = seed;
+  params.use_diffusion_curve_save = ingest.use_diffusion_curve_save;
+  params.use_aa = use_aa;
+  params.max_trace_depth = max_depth;
+  params.traversal = brute ? RDC_TRAVERSAL_BRUTE_FORCE : RDC_TRAVERSAL_LBVH;
+
+  float* host_image = nullptr;
+  CALL_CHECK((int)cudaMallocHost((void**)&host_image, sizeof(float) * 4 * (size_t)width * height));
+  CALL_CHECK((int)cudaStreamSynchronize(stream));
+  auto setup_ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - start_time);
+  std::cout << "Setup took : " << setup_ms.count() << " ms" << std::endl;
+  std::cout << "Scene : " << info.n_curves << " curves, " << info.n_segments << " segments, " << info.n_chords
+            << " chords, tree depth " << info.bvh_depth << std::endl;
+
+  double total_ms = 0.0;
+  for (int f = 0; f < frames; ++f) {
+    auto t0 = std::chrono::high_resolution_clock::now();
+    params.frame = (uint32_t)f;
+    CALL_CHECK(rdc_render_frame_to_host(scene, &params, use_blur ? 1 : 0, host_image, stream));
+    printf("\rframe : %d", f + 1);
+    fflush(stdout);
+    total_ms += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+  }
+  std::cout << std::endl;
+  const double avg_ms = total_ms / frames;
+  std::cout << "Average frame time  : " << avg_ms << " ms" << std::endl;
+  std::cout << "Throughput : " << (double)width * height * number_of_rays / (avg_ms * 1e-3) / 1e9 << " Grays/s" << std::endl;
+
+  if (!out_path.empty()) {
+    std::vector<uint8_t> rgba((size_t)4 * width * height);
+    // Orzan saves are rendered bottom-up (DeviceCode.cu:104-105) and shown with glDrawPixels; the
+    // screenshot flips them into a top-down file (glfw_events.cpp:92). Same rule here.
+    CALL_CHECK(rdc_image_to_rgba8(host_image, width, height, ingest.use_diffusion_curve_save ? 1 : 0, rgba.data()));
+    CALL_CHECK(rdc_write_ppm(out_path.c_str(), rgba.data(), width, height));
+    std::cout << "Wrote " << out_path << std::endl;
+  }
+  cudaFreeHost(host_image);
+  rdc_scene_destroy(scene);
+  rdc_host_scene_destroy(host);
+  cudaStreamDestroy(stream);
+  return 0;
+}

@@ -1,0 +1,404 @@
+// render.cu — per-frame ray generation, closest-chord traversal, shading, weighted normalisation.
+//
+// Replaces optixLaunch(...) of DeviceCode.cu's three programs (optixHello.cpp:1184):
+//   __raygen__rg      DeviceCode.cu:85-182   -> k_render's pixel loop
+//   __closesthit__ch  DeviceCode.cu:194-342  -> shade_hit (terminal :328-340, portal :220-320 as an
+//                                               iterative re-trace loop, shape of DeviceCodeIt.cu:151-170)
+//   __miss__ms        DeviceCode.cu:185-192  -> zero contribution
+//   RT-core traversal + built-in curve intersector (closed) -> closest_chord over the LBVH of accel.cu
+// Compiled with -fmad=false: plain expressions keep the reference's operation order and rounding; fused
+// operations appear only through rdc_fma (rdc_math.h).
+#include <cstdio>
+
+#include "device_scene.h"
+#include "rdc_math.h"
+
+namespace rdc {
+namespace {
+
+constexpr int kTileW = 16, kTileH = 16, kBlock = kTileW * kTileH;
+constexpr int kStack = 64;
+constexpr uint32_t kMiss = 0xFFFFFFFFu;
+constexpr size_t kSmemSceneLimit = 32 * 1024;  // stage nodes + chords in shared memory below this
+
+struct RenderArgs {
+  DevScene sc;
+  float4* image;
+  float* blur_map;
+  const float2* base_dirs;
+  uint32_t* hit_ids;
+  float* max_sigma;
+  uint32_t width, height, row_begin, row_end;
+  int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
+  float two_over_n;   // 2 / number_of_rays_per_pixel  (DeviceCode.cu:99,120)
+  float zoom, off_x, off_y;
+  uint32_t frame, seed;
+  int orzan, use_aa, max_depth, brute;
+};
+
+struct Hit {
+  float t, s;
+  int leaf;      // position in Morton order, -1 = miss
+  uint32_t id;   // original chord id (tie-break, parity)
+};
+
+struct Accel {
+  const BvhNode* nodes;
+  const float4* geom;
+  const uint4* ids;
+  uint32_t n_chords;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ float4 load16(const float4* p) {
+  if (SMEM) return *p;
+  return __ldg(p);
+}
+
+template <bool SMEM, bool PORTALS>
+__device__ __forceinline__ void test_chord(const Accel& ac, int leaf, float ox, float oy, float dx, float dy,
+                                           float inv_dd, uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
+  float4 g = load16<SMEM>(ac.geom + leaf);
+  float t, s;
+  if (!rdc_ray_chord(ox, oy, dx, dy, inv_dd, g.x, g.y, g.z, g.w, &t, &s)) return;
+  if (t > h.t) return;
+  uint32_t id = __ldg(&ac.ids[leaf].x);
+  if (PORTALS && id >= skip_lo && id <= skip_hi) return;
+  if (rdc_hit_closer(t, id, h.t, h.id)) {
+    h.t = t; h.s = s; h.leaf = leaf; h.id = id;
+  }
+}
+
+// Closest chord along the ray. Ordered depth-first traversal: the nearer child first, the farther one on
+// a per-thread stack; a child is entered when the ray's interval inside its box starts before the best
+// hit so far (with RDC_CULL_SLACK). Leaves are tested as soon as their box is hit.
+template <bool SMEM, bool PORTALS>
+__device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
+                                             uint32_t skip_lo, uint32_t skip_hi) {
+  Hit h;
+  h.t = __int_as_float(0x7f800000);
+  h.s = 0.0f;
+  h.leaf = -1;
+  h.id = kMiss;
+  const float inv_dd = 1.0f / (dx * dx + dy * dy);
+  if (brute) {
+    for (uint32_t c = 0; c < ac.n_chords; ++c) test_chord<SMEM, PORTALS>(ac, (int)c, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+    return h;
+  }
+  const float idx = rdc_safe_inv(dx), idy = rdc_safe_inv(dy);
+  int stack[kStack];
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
+    float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
+    float4 ch = load16<SMEM>(np + 2);
+    int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+    float le, re;
+    float ln = rdc_slab(ox, oy, idx, idy, lb.x, lb.y, lb.z, lb.w, &le);
+    float rn = rdc_slab(ox, oy, idx, idy, rb.x, rb.y, rb.z, rb.w, &re);
+    float lim = h.t * RDC_CULL_SLACK;
+    bool hl = ln <= le && ln <= lim;
+    bool hr = rn <= re && rn <= lim;
+    if (hl && left < 0) {
+      test_chord<SMEM, PORTALS>(ac, ~left, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      hl = false;
+    }
+    if (hr && right < 0) {
+      // the left leaf may just have shortened the ray
+      if (rn <= h.t * RDC_CULL_SLACK) test_chord<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      hr = false;
+    }
+    if (hl && hr) {
+      bool left_first = ln <= rn;
+      stack[sp++] = left_first ? right : left;
+      node = left_first ? left : right;
+    } else if (hl) {
+      node = left;
+    } else if (hr) {
+      node = right;
+    } else {
+      if (sp == 0) break;
+      node = stack[--sp];
+    }
+  }
+  return h;
+}
+
+__device__ __forceinline__ void load_control_points(const DevScene& sc, uint32_t seg, rdc_f2 v[4]) {
+  const float4* p = reinterpret_cast<const float4*>(sc.vertices + __ldg(sc.segment_indices + seg));
+  float4 a = __ldg(p), b = __ldg(p + 1);
+  v[0] = {a.x, a.y};
+  v[1] = {a.z, a.w};
+  v[2] = {b.x, b.y};
+  v[3] = {b.z, b.w};
+}
+
+__device__ __forceinline__ float scalar_stop(const DevStops& st, uint32_t curve, float cu) {
+  uint2 ix = __ldg(st.index + curve);
+  float ratio;
+  int ind = rdc_interp(ix.x, ix.y, cu, st.u, &ratio);
+  return rdc_lerp_stop(__ldg(st.value + ind), __ldg(st.value + ind + 1), ratio);
+}
+
+// `ix` selects the walk range, `us`/`rgb` the arrays (the portal filter mixes families, DeviceCode.cu:297)
+__device__ __forceinline__ void colour_stop(uint2 ix, const float* us, const float4* rgb, float cu, float& r, float& g,
+                                            float& b) {
+  float ratio;
+  int ind = rdc_interp(ix.x, ix.y, cu, us, &ratio);
+  float4 c0 = __ldg(rgb + ind), c1 = __ldg(rgb + ind + 1);
+  r = rdc_lerp_color(c0.x, c1.x, ratio);
+  g = rdc_lerp_color(c0.y, c1.y, ratio);
+  b = rdc_lerp_color(c0.z, c1.z, ratio);
+}
+
+struct Sample {
+  float r, g, b, w, blur;
+};
+
+// One primary ray through any number of portals (DeviceCode.cu:194-342, iteratively).
+// Carried state: F = product of portal filters, Bp = product of portal blurs, S = sum of 1/w_portal;
+// terminal hit: rgb = F*rgb_T, blur = Bp*blur_T, w = 1/(1/w_T + S) — the closed form of the reference's
+// recursion w = 1/(1/w' + 1/w_here) (:310).
+template <bool SMEM, bool PORTALS>
+__device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac, float ox, float oy, float dx, float dy,
+                                            uint32_t& first_hit) {
+  const DevScene& sc = a.sc;
+  Sample out{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  float Fr = 1.0f, Fg = 1.0f, Fb = 1.0f, Bp = 1.0f, S = 0.0f;
+  int depth = 0;
+  uint32_t skip_lo = 1, skip_hi = 0;  // empty range
+  first_hit = kMiss;
+  for (;;) {
+    Hit h = closest_chord<SMEM, PORTALS>(ac, a.brute != 0, ox, oy, dx, dy, skip_lo, skip_hi);
+    if (depth == 0) first_hit = h.id;
+    if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
+    uint4 id = __ldg(ac.ids + h.leaf);
+    const uint32_t seg = id.y;
+    const float u = rdc_hit_u((int)id.z, (int)id.w, h.s);
+    const uint32_t curve = __ldg(sc.curve_map + seg);
+    const uint32_t ordinal = __ldg(sc.curve_index + seg);
+    const float cu = u + ordinal;
+    const float blur_here = scalar_stop(sc.blur, curve, cu);
+    const float wm = scalar_stop(sc.weight, curve, cu);
+    const float e = scalar_stop(sc.weight_degree, curve, cu);
+    const float w_here = wm * rdc_weight_falloff(h.t, e);
+    rdc_f2 v[4];
+    load_control_points(sc, seg, v);
+    const bool right = rdc_is_ray_right(u, dx, dy, v[0], v[1], v[2], v[3], a.orzan != 0);
+
+    if (PORTALS) {
+      const int target_curve = __ldg(sc.curve_connect + curve);
+      if (target_curve >= 0) {
+        if (++depth > a.max_depth) return out;  // depth cap: regarded as a miss (:313-320)
+        const uint32_t tseg = __ldg(sc.curve_map_inverse + target_curve) + ordinal;
+        rdc_f2 tv[4];
+        load_control_points(sc, tseg, tv);
+        rdc_f2 o2 = rdc_spline_point(u, tv[0], tv[1], tv[2], tv[3]);
+        rdc_f2 n = rdc_spline_normal(u, v[0], v[1], v[2], v[3]);
+        float nl = sqrtf(n.x * n.x + n.y * n.y);
+        n.x /= nl; n.y /= nl;
+        float rc = n.x * dx + n.y * dy;
+        float rs = n.x * dy + n.y * dx;  // sic (:243)
+        rdc_f2 m = rdc_spline_normal(u, tv[0], tv[1], tv[2], tv[3]);
+        float ml = sqrtf(m.x * m.x + m.y * m.y);
+        m.x /= ml; m.y /= ml;
+        float ndx = m.x * rc - m.y * rs;
+        float ndy = m.y * rc + m.x * rs;
+        float fr, fg, fb;
+        uint2 rix = __ldg(sc.color_right.index + curve);
+        if (right) colour_stop(rix, sc.color_right.u, sc.color_right.rgb, cu, fr, fg, fb);
+        else colour_stop(rix, sc.color_left.u, sc.color_left.rgb, cu, fr, fg, fb);  // right index on left arrays (:297)
+        Fr *= fr; Fg *= fg; Fb *= fb;
+        Bp *= blur_here;
+        S += 1.0f / w_here;
+        int klo, khi;
+        const int Kt = (int)__ldg(sc.seg_chord_count + tseg);
+        rdc_portal_skip(u, Kt, &klo, &khi);
+        const uint32_t tbase = __ldg(sc.seg_chord_base + tseg);
+        skip_lo = tbase + (uint32_t)klo;
+        skip_hi = tbase + (uint32_t)khi;
+        ox = o2.x; oy = o2.y; dx = ndx; dy = ndy;
+        continue;
+      }
+    }
+    float r, g, b;
+    if (right) colour_stop(__ldg(sc.color_right.index + curve), sc.color_right.u, sc.color_right.rgb, cu, r, g, b);
+    else colour_stop(__ldg(sc.color_left.index + curve), sc.color_left.u, sc.color_left.rgb, cu, r, g, b);
+    if (PORTALS && depth > 0) {
+      out.r = Fr * r; out.g = Fg * g; out.b = Fb * b;
+      out.blur = Bp * blur_here;
+      out.w = 1.0f / (1.0f / w_here + S);
+    } else {
+      out.r = r; out.g = g; out.b = b;
+      out.blur = blur_here;
+      out.w = w_here;
+    }
+    return out;
+  }
+}
+
+// Base direction of ray i: (1,0) rotated i times by the fp32 matrix of sincospi(2/N) — iterated, because
+// the accumulated rounding is part of the ray set (DeviceCode.cu:99,110-112,167-171). Pixel-independent,
+// so it is tabulated once per N.
+__global__ void k_base_dirs(float2* out, int n_iter, float two_over_n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float rs, rc;
+  rdc_sincospi(two_over_n, &rs, &rc);
+  float x = 1.0f, y = 0.0f;
+  for (int i = 0; i < n_iter; ++i) {
+    out[i] = make_float2(x, y);
+    float nx = x * rc - y * rs;
+    float ny = x * rs + y * rc;
+    x = nx; y = ny;
+  }
+}
+
+template <bool SMEM, bool PORTALS>
+__global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
+  extern __shared__ uint4 smem[];
+  Accel ac;
+  ac.ids = a.sc.chord_ids;
+  ac.n_chords = a.sc.n_chords;
+  if (SMEM) {
+    const uint32_t node_words = a.sc.n_nodes * (uint32_t)(sizeof(BvhNode) / 16);
+    const uint4* gn = reinterpret_cast<const uint4*>(a.sc.nodes);
+    const uint4* gg = reinterpret_cast<const uint4*>(a.sc.chord_geom);
+    for (uint32_t i = threadIdx.x; i < node_words; i += kBlock) smem[i] = __ldg(gn + i);
+    for (uint32_t i = threadIdx.x; i < a.sc.n_chords; i += kBlock) smem[node_words + i] = __ldg(gg + i);
+    __syncthreads();
+    ac.nodes = reinterpret_cast<const BvhNode*>(smem);
+    ac.geom = reinterpret_cast<const float4*>(smem + node_words);
+  } else {
+    ac.nodes = a.sc.nodes;
+    ac.geom = a.sc.chord_geom;
+  }
+
+  // 16x16 pixel tile per block, 8x4 pixels per warp
+  const uint32_t tiles_x = (a.width + kTileW - 1) / kTileW;
+  const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ix = tile_x * kTileW + (warp & 1) * 8 + (lane & 7);
+  const uint32_t ly = tile_y * kTileH + (warp >> 1) * 4 + (lane >> 3);  // row inside the band
+  const uint32_t iy = a.row_begin + ly;                                // row of the full image
+  const bool valid = ix < a.width && iy < a.row_end;
+
+  float sigma = 0.0f;
+  if (valid) {
+    // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
+    const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
+    const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
+                                 : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
+    const uint32_t pixel = iy * a.width + ix;  // global pixel index: band-independent random numbers
+    const size_t local_pixel = (size_t)ly * a.width + ix;
+    float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
+    for (int i = 0; i < a.n_iter; ++i) {
+      const float2 base = __ldg(a.base_dirs + i);
+      // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
+      const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
+      float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
+      if (a.use_aa) {
+        float js, jc;
+        rdc_sincospi(a.two_over_n * rdc_u01(rnd.x), &js, &jc);
+        dx = base.x * jc - base.y * js;
+        dy = base.x * js + base.y * jc;
+        ox = base_x + rdc_u01(rnd.y) * a.zoom;
+        oy = base_y + rdc_u01(rnd.z) * a.zoom;
+      }
+      uint32_t first_hit;
+      Sample s = trace_ray<SMEM, PORTALS>(a, ac, ox, oy, dx, dy, first_hit);
+      if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
+      weight_total += s.w;
+      cr += s.r * s.w;
+      cg += s.g * s.w;
+      cb += s.b * s.w;
+      blur += s.blur * s.w;
+    }
+    // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
+    a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
+    sigma = blur / weight_total;
+    a.blur_map[local_pixel] = sigma;
+  }
+  if (a.max_sigma) {
+    // NaN and negative sigmas do not raise the flag: such pixels produce NaN in the blur either way
+    unsigned int bits = __float_as_uint(fmaxf(sigma, 0.0f));
+    bits = __reduce_max_sync(0xFFFFFFFFu, bits);
+    if (lane == 0 && bits != 0u) atomicMax(reinterpret_cast<unsigned int*>(a.max_sigma), bits);
+  }
+}
+
+}  // namespace
+
+int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream) {
+  if (!s || !image || !blur_map) {
+    set_error("render: null argument");
+    return RDC_E_INVALID;
+  }
+  if (p.image_width == 0 || p.image_height == 0 || p.row_begin >= p.row_end || p.row_end > p.image_height) {
+    set_error("render: bad image size or row band [%u,%u) of %u", p.row_begin, p.row_end, p.image_height);
+    return RDC_E_INVALID;
+  }
+  if (!(p.number_of_rays_per_pixel >= 1.0f) || p.number_of_rays_per_pixel > 65536.0f) {
+    set_error("render: rays per pixel must be in [1, 65536]");
+    return RDC_E_INVALID;
+  }
+  if (p.max_trace_depth < 0 || p.max_trace_depth > 31) {
+    set_error("render: max_trace_depth must be in [0, 31]");
+    return RDC_E_INVALID;
+  }
+  if ((uint64_t)p.image_width * p.image_height > 0xFFFFFFFFull) {
+    set_error("render: more than 2^32 pixels");
+    return RDC_E_LIMIT;
+  }
+  const int n_iter = (int)ceilf(p.number_of_rays_per_pixel);
+  if (s->base_dirs_n != p.number_of_rays_per_pixel) {
+    if ((uint32_t)n_iter > s->base_dirs_capacity) {
+      float2* fresh = nullptr;
+      RDC_CUDA(cudaMalloc(&fresh, (size_t)n_iter * sizeof(float2)));
+      s->allocations.push_back(fresh);
+      s->base_dirs = fresh;
+      s->base_dirs_capacity = (uint32_t)n_iter;
+    }
+    k_base_dirs<<<1, 32, 0, stream>>>(s->base_dirs, n_iter, 2 / p.number_of_rays_per_pixel);
+    RDC_CUDA(cudaGetLastError());
+    s->base_dirs_n = p.number_of_rays_per_pixel;
+  }
+
+  RenderArgs a{};
+  a.sc = s->dev;
+  a.image = image;
+  a.blur_map = blur_map;
+  a.base_dirs = s->base_dirs;
+  a.hit_ids = p.hit_ids;
+  a.max_sigma = p.max_sigma;
+  a.width = p.image_width;
+  a.height = p.image_height;
+  a.row_begin = p.row_begin;
+  a.row_end = p.row_end;
+  a.n_iter = n_iter;
+  a.two_over_n = 2 / p.number_of_rays_per_pixel;
+  a.zoom = p.zoom_factor;
+  a.off_x = p.offset_x;
+  a.off_y = p.offset_y;
+  a.frame = p.frame;
+  a.seed = p.seed;
+  a.orzan = p.use_diffusion_curve_save;
+  a.use_aa = p.use_aa;
+  a.max_depth = p.max_trace_depth;
+  a.brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
+
+  const uint32_t rows = p.row_end - p.row_begin;
+  const uint32_t tiles = ((p.image_width + kTileW - 1) / kTileW) * ((rows + kTileH - 1) / kTileH);
+  const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_chords * sizeof(float4);
+  const bool smem = scene_bytes <= kSmemSceneLimit;
+  const bool portals = s->info.has_portals != 0;
+  const size_t dyn = smem ? scene_bytes : 0;
+  if (smem && portals) k_render<true, true><<<tiles, kBlock, dyn, stream>>>(a);
+  else if (smem) k_render<true, false><<<tiles, kBlock, dyn, stream>>>(a);
+  else if (portals) k_render<false, true><<<tiles, kBlock, 0, stream>>>(a);
+  else k_render<false, false><<<tiles, kBlock, 0, stream>>>(a);
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rdc
