@@ -2,7 +2,7 @@
 # the CPU oracle under oracle/ (test infrastructure). `python -c "import __graft_entry__ as g; g.build()"`
 # runs the same recipes.
 NVCC      ?= nvcc
-CXX       ?= g++
+CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 PKG       := raytracingdiffusioncurves_b200
 CSRC      := $(PKG)/csrc
 BUILD     := build
@@ -13,7 +13,7 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Iinclude
 
 LIB       := $(PKG)/librdc_b200.so
 CLI       := $(PKG)/OptixHello
-CU_SRCS   := $(CSRC)/accel.cu $(CSRC)/render.cu $(CSRC)/blur.cu $(CSRC)/capi.cu
+CU_SRCS   := $(CSRC)/accel.cu $(CSRC)/render.cu $(CSRC)/blur.cu $(CSRC)/capi.cu $(CSRC)/microbench.cu
 CPP_SRCS  := $(CSRC)/xml_dom.cpp $(CSRC)/ingest.cpp $(CSRC)/synth.cpp
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.cpp.o,$(CPP_SRCS))

@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native diffusion-curve ray tracer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one frame of the hot path: ray generation + closest-hit traversal + shading + normalisation
+(`rdc_render`) followed by the variable-sigma blur (`rdc_gaussian_blur`), on BASELINE.json's configs[1]:
+xmls/arch.xml at 1920x1080, 128 rays per pixel, Orzan flag / blur / per-ray jitter as shipped, denoiser
+off. The metric is Grays/s = primary rays per second (W*H*rpp / t_frame / 1e9), whole job.
+
+N > 1: the image is cut into contiguous row bands, one per rank, scene + LBVH replicated; after rendering
+every rank sends its band to rank 0 (NCCL gather over NVLink) and rank 0 blurs the assembled frame. Total
+work is fixed as N grows ("strong" scaling); the gather is inside the timed region.
+
+Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, width, height, rays per pixel, max trace depth)
+    "arch_1080p_128rpp": ("xml:arch.xml", 1920, 1080, 128, 2),            # BASELINE.json configs[1] (headline)
+    "arch_512_128rpp": ("xml:arch.xml", 512, 512, 128, 2),                # configs[0]
+    "portal_1080p_depth31": ("xml:PortalDemo.xml", 1920, 1080, 128, 31),  # configs[3]
+    "synth100k_8k_512rpp": ("synth:100000:8192", 8192, 8192, 512, 2),     # configs[4]
+    "synth100k_2k_64rpp": ("synth:100000:8192", 2048, 2048, 64, 2),       # configs[4] geometry, smaller frame
+}
+DEFAULT_WORKLOAD = "arch_1080p_128rpp"
+XML_DIR = os.path.join(ROOT, "tests", "golden", "xmls")
+
+# algorithmic work per ray, FMA = 2 flops
+F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def scene_source(spec):
+    """Returns (kind, payload): ('file', path) or ('text', xml bytes)."""
+    kind, _, rest = spec.partition(":")
+    if kind == "xml":
+        return "file", os.path.join(XML_DIR, rest)
+    n, size = rest.split(":")
+    from raytracingdiffusioncurves_b200 import api
+
+    return "text", api.synth_xml(int(n), int(size), int(size))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_oracle_run(kind_pref, scene_spec, width, height, rpp, depth, zoom, target_seconds):
+    """Times the CPU implementation on a bounded band of the workload. Returns the cpu_baseline dict."""
+    from oracle import pyoracle as po
+
+    kind = kind_pref if (kind_pref == "port" or po.Oracle.reference_available()) else "port"
+    if kind == "reference" and depth != 2:
+        kind = "port"  # the reference build is compiled with MAX_TRACE_DEPTH 2
+    oracle = po.Oracle(kind)
+    skind, payload = scene_source(scene_spec)
+    if skind == "text":
+        path = "/tmp/rdc_bench_synth.xml"
+        with open(path, "wb") as fh:
+            fh.write(payload)
+    else:
+        path = payload
+    scene = po.ingest_xml(path, True)
+    mid = height // 2
+
+    def run(rows):
+        b = max(0, mid - rows // 2)
+        p = po.make_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, row_begin=b, row_end=min(height, b + rows))
+        t0 = time.perf_counter()
+        oracle.render(scene, p)
+        return time.perf_counter() - t0, (p.row_end - p.row_begin)
+
+    t_probe, rows_probe = run(max(oracle.threads(), 8))
+    rows = int(max(rows_probe, min(height, rows_probe * target_seconds / max(t_probe, 1e-6))))
+    t, rows = run(rows)
+    rays = float(rows) * width * rpp
+    return {
+        "value": rays / t / 1e9, "unit": "Grays/s", "cores": oracle.threads(),
+        "kind": "reference" if kind == "reference" else "port",
+        "sample": f"{rows} centre rows of the {width}x{height}@{rpp} frame ({rays / 1e6:.1f} M rays, {t:.1f} s), render only, "
+                  + ("reference DeviceCode.cu compiled for the host (oracle/_ref)" if kind == "reference"
+                     else "restated oracle (oracle/oracle_port.cpp)") + ", brute-force closest hit, OpenMP",
+        "ms_per_frame_extrapolated": t / rows * height * 1e3,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU-runnable implementation of the path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, width, height, rpp, depth = WORKLOADS[args.workload]
+    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
+    per_step_seconds = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    results = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, per_step_seconds)
+        if i >= args.warmup:
+            results.append(r)
+    value = sum(r["value"] for r in results) / len(results)
+    base = results[-1]
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": "Grays/s", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(width) * height * rpp / (value * 1e9) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "bundled scene file" if spec.startswith("xml:") else "synthetic",
+        "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp,
+                   "note": "each step times a bounded band of the frame on the host cores; ms_per_step is the extrapolated full frame"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from raytracingdiffusioncurves_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    spec, width, height, rpp, depth = WORKLOADS[args.workload]
+    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
+    kind, payload = scene_source(spec)
+    t_setup = time.perf_counter()
+    host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
+    scene = api.Scene(host.arrays, None, stream)
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t_setup) * 1e3
+
+    row_begin, row_end = api.row_band(height, rank, world)
+    rows = row_end - row_begin
+    max_rows = api.row_band(height, 0, world)[1]
+    band = torch.empty((max_rows, width, 4), dtype=torch.float32, device=dev)
+    sigma_band = torch.empty((max_rows, width), dtype=torch.float32, device=dev)
+    flag = torch.zeros((1,), dtype=torch.float32, device=dev)
+    if rank == 0:
+        frame = torch.empty((world * max_rows, width, 4), dtype=torch.float32, device=dev) if world > 1 else band
+        sigma = torch.empty((world * max_rows, width), dtype=torch.float32, device=dev) if world > 1 else sigma_band
+        scratch = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
+        out_frame = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def params_for(step, **kw):
+        return api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=step,
+                                        row_begin=row_begin, row_end=row_end, **kw)
+
+    def frame_step(step):
+        """One frame, inputs resident: render band -> (gather) -> blur on rank 0."""
+        flag.zero_()
+        p = params_for(step)
+        p.max_sigma = flag.data_ptr()
+        scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
+        if world > 1:
+            # bands are equal-sized up to one row; pad to max_rows so one gather moves them all
+            dist.gather(band, list(frame.view(world, max_rows, width, 4).unbind(0)) if rank == 0 else None, dst=0)
+            dist.gather(sigma_band, list(sigma.view(world, max_rows, width).unbind(0)) if rank == 0 else None, dst=0)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            if world > 1 and height % world != 0:
+                raise SystemExit("bench.py: image height must divide by the number of GPUs")
+            api.gaussian_blur(out_frame.data_ptr(), frame.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), width, height, 0, height,
+                              flag.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-timed, inputs resident, L2 flushed between steps ----------------------------
+    for s in range(args.warmup):
+        frame_step(s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (untimed)
+        starts[s].record()
+        frame_step(args.warmup + s)
+        ends[s].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop_flag = True
+    sampler.join()
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    rays_per_frame = float(width) * height * rpp
+    value = rays_per_frame / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: the public host-buffer call (params in, pinned image out), every step ---------------
+    e2e = None
+    if world == 1:
+        host_img = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
+        n_e2e = max(3, min(args.steps, 50))
+        for s in range(2):
+            scene.render_frame_to_host(params_for(s), True, host_img.data_ptr(), stream)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(n_e2e):
+            scene.render_frame_to_host(params_for(1000 + s), True, host_img.data_ptr(), stream)
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
+               "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams), "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
+               "api": "rdc_render_frame_to_host (render + blur + copy to pinned host memory + stream sync)"}
+
+    # ---- roofline of the dominant kernel (k_render), measured live ---------------------------------
+    roofline = None
+    if rank == 0:
+        # work per ray from the counting build (one frame)
+        stats = torch.zeros((4,), dtype=torch.int64, device=dev)
+        p = params_for(0)
+        p.stats = stats.data_ptr()
+        scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
+        torch.cuda.synchronize()
+        traced, nodes, chords, shaded = [float(x) for x in stats.cpu().tolist()]
+        band_rays = float(rows) * width * rpp
+        n_node, n_seg, n_hit = nodes / band_rays, chords / band_rays, shaded / band_rays
+        f_ray = F_GEN + n_node * F_NODE + n_seg * F_SEG + n_hit * F_SHADE + F_ACC
+        # the kernel alone, CUDA events on its stream
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(5, min(args.steps, 30))
+        pk = params_for(1)
+        pk.max_sigma = flag.data_ptr()
+        k0.record()
+        for _ in range(reps):
+            scene.render(pk, band.data_ptr(), sigma_band.data_ptr(), stream)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / reps
+        # FP32 peak: dependent-FFMA microbenchmark on the same box, same moment
+        sink = torch.zeros((4,), dtype=torch.float32, device=dev)
+        flops = ctypes.c_double()
+        api.lib.rdc_microbench_fp32(2048, 2, sink.data_ptr(), ctypes.byref(flops), stream)
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        api.lib.rdc_microbench_fp32(2048, 10, sink.data_ptr(), ctypes.byref(flops), stream)
+        m1.record()
+        torch.cuda.synchronize()
+        fp32_peak = flops.value * 10 / (m0.elapsed_time(m1) * 1e-3) / 1e12
+        achieved = band_rays * f_ray / (kernel_ms * 1e-3) / 1e12
+        hbm_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = json.load(fh).get("hbm_gbs")
+        except Exception:
+            pass
+        alg_bytes = float(rows) * width * 20.0
+        roofline = {
+            "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp32_peak, "traffic": None,
+            "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
+            "kernel_ms": kernel_ms, "flops_per_ray": f_ray,
+            "per_ray": {"nodes": n_node, "chords": n_seg, "hits_shaded": n_hit, "rays_traced": traced / band_rays},
+            "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                    "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound"},
+        }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, args.cpu_seconds)
+
+    if rank == 0:
+        st = scene.stats
+        line = {
+            "metric": "Grays/s", "value": value, "unit": "Grays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
+            "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
+                       "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
+                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
+                       "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+            "clocks": sampler.result(),
+            "e2e": e2e,
+            "gpu_launches": 3 * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,10 @@ typedef struct rdc_frame_params {
                                            ray's first hit, 0xFFFFFFFF for a miss (parity tests)       */
   float* max_sigma;                     /* optional device float: atomically raised to the largest
                                            blur_map value written (lets the blur skip all-zero maps)   */
+  unsigned long long* stats;            /* optional device uint64[4], atomically increased by: rays traced
+                                           (continuations included), tree nodes visited, chords tested,
+                                           hits shaded. Selects a slower counting build of the kernel;
+                                           feeds the roofline's work-per-ray figure      */
 } rdc_frame_params;
 
 void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t height, float rays_per_pixel);
@@ -156,6 +160,11 @@ int rdc_write_ppm(const char* path, const uint8_t* rgba, int width, int height);
  *      emitted as XML text in the reference's schema so it passes through the same loader.
  *      Caller frees *out_text with rdc_free. ---- */
 int rdc_synth_xml(uint32_t n_curves, uint32_t width, uint32_t height, uint64_t seed, char** out_text, size_t* out_len);
+
+/* ---- measurement aid: dependent-FFMA microbenchmark used as the FP32 roofline denominator.
+ *      Launches `launches` kernels of 148*8 blocks x 256 threads, each thread doing iters*64 FFMAs, on
+ *      `stream`; returns the flop count of ONE launch in *flops_per_launch. Enqueue-only. ---- */
+int rdc_microbench_fp32(int iters, int launches, float* sink, double* flops_per_launch, rdc_stream stream);
 
 const char* rdc_last_error_string(void);
 const char* rdc_version(void);

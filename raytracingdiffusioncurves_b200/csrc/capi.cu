@@ -183,6 +183,7 @@ void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t heig
   p->traversal = RDC_TRAVERSAL_LBVH;
   p->hit_ids = nullptr;
   p->max_sigma = nullptr;
+  p->stats = nullptr;
 }
 
 int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream) {
@@ -284,7 +285,8 @@ int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint
     const float* src = image + (size_t)4 * width * y;
     uint8_t* dst = out + (size_t)4 * width * (flip ? height - 1 - y : y);
     for (int i = 0; i < 4 * width; ++i) {
-      float v = std::fmin(src[i] * 255, 255.0f);
+      float v = src[i] * 255;
+      if (v > 255.0f) v = 255.0f;
       dst[i] = (v == v && v > 0.0f) ? (uint8_t)v : 0;  // NaN (all rays missed) and negatives -> 0
     }
   }

@@ -28,6 +28,7 @@ struct RenderArgs {
   const float2* base_dirs;
   uint32_t* hit_ids;
   float* max_sigma;
+  unsigned long long* stats;
   uint32_t width, height, row_begin, row_end;
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
   float two_over_n;   // 2 / number_of_rays_per_pixel  (DeviceCode.cu:99,120)
@@ -47,6 +48,11 @@ struct Accel {
   const float4* geom;
   const uint4* ids;
   uint32_t n_chords;
+};
+
+// per-thread work counters of the counting build (rdc_frame_params::stats)
+struct Counters {
+  unsigned int rays = 0, nodes = 0, chords = 0, shaded = 0;
 };
 
 template <bool SMEM>
@@ -72,10 +78,11 @@ __device__ __forceinline__ void test_chord(const Accel& ac, int leaf, float ox, 
 // Closest chord along the ray. Ordered depth-first traversal: the nearer child first, the farther one on
 // a per-thread stack; a child is entered when the ray's interval inside its box starts before the best
 // hit so far (with RDC_CULL_SLACK). Leaves are tested as soon as their box is hit.
-template <bool SMEM, bool PORTALS>
+template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
-                                             uint32_t skip_lo, uint32_t skip_hi) {
+                                             uint32_t skip_lo, uint32_t skip_hi, Counters& cnt) {
   Hit h;
+  if (STATS) cnt.rays++;
   h.t = __int_as_float(0x7f800000);
   h.s = 0.0f;
   h.leaf = -1;
@@ -83,6 +90,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   const float inv_dd = 1.0f / (dx * dx + dy * dy);
   if (brute) {
     for (uint32_t c = 0; c < ac.n_chords; ++c) test_chord<SMEM, PORTALS>(ac, (int)c, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+    if (STATS) cnt.chords += ac.n_chords;
     return h;
   }
   const float idx = rdc_safe_inv(dx), idy = rdc_safe_inv(dy);
@@ -90,6 +98,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   int sp = 0;
   int node = 0;
   for (;;) {
+    if (STATS) cnt.nodes++;
     const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
     float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
     float4 ch = load16<SMEM>(np + 2);
@@ -101,12 +110,16 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
     bool hl = ln <= le && ln <= lim;
     bool hr = rn <= re && rn <= lim;
     if (hl && left < 0) {
+      if (STATS) cnt.chords++;
       test_chord<SMEM, PORTALS>(ac, ~left, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
       hl = false;
     }
     if (hr && right < 0) {
       // the left leaf may just have shortened the ray
-      if (rn <= h.t * RDC_CULL_SLACK) test_chord<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      if (rn <= h.t * RDC_CULL_SLACK) {
+        if (STATS) cnt.chords++;
+        test_chord<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      }
       hr = false;
     }
     if (hl && hr) {
@@ -160,9 +173,9 @@ struct Sample {
 // Carried state: F = product of portal filters, Bp = product of portal blurs, S = sum of 1/w_portal;
 // terminal hit: rgb = F*rgb_T, blur = Bp*blur_T, w = 1/(1/w_T + S) — the closed form of the reference's
 // recursion w = 1/(1/w' + 1/w_here) (:310).
-template <bool SMEM, bool PORTALS>
+template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac, float ox, float oy, float dx, float dy,
-                                            uint32_t& first_hit) {
+                                            uint32_t& first_hit, Counters& cnt) {
   const DevScene& sc = a.sc;
   Sample out{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   float Fr = 1.0f, Fg = 1.0f, Fb = 1.0f, Bp = 1.0f, S = 0.0f;
@@ -170,9 +183,10 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
   uint32_t skip_lo = 1, skip_hi = 0;  // empty range
   first_hit = kMiss;
   for (;;) {
-    Hit h = closest_chord<SMEM, PORTALS>(ac, a.brute != 0, ox, oy, dx, dy, skip_lo, skip_hi);
+    Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, skip_lo, skip_hi, cnt);
     if (depth == 0) first_hit = h.id;
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
+    if (STATS) cnt.shaded++;
     uint4 id = __ldg(ac.ids + h.leaf);
     const uint32_t seg = id.y;
     const float u = rdc_hit_u((int)id.z, (int)id.w, h.s);
@@ -254,7 +268,7 @@ __global__ void k_base_dirs(float2* out, int n_iter, float two_over_n) {
   }
 }
 
-template <bool SMEM, bool PORTALS>
+template <bool SMEM, bool PORTALS, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
   extern __shared__ uint4 smem[];
   Accel ac;
@@ -284,6 +298,7 @@ __global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
   const bool valid = ix < a.width && iy < a.row_end;
 
   float sigma = 0.0f;
+  Counters cnt;
   if (valid) {
     // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
     const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
         oy = base_y + rdc_u01(rnd.z) * a.zoom;
       }
       uint32_t first_hit;
-      Sample s = trace_ray<SMEM, PORTALS>(a, ac, ox, oy, dx, dy, first_hit);
+      Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
       if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
       weight_total += s.w;
       cr += s.r * s.w;
@@ -324,6 +339,16 @@ __global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
     unsigned int bits = __float_as_uint(fmaxf(sigma, 0.0f));
     bits = __reduce_max_sync(0xFFFFFFFFu, bits);
     if (lane == 0 && bits != 0u) atomicMax(reinterpret_cast<unsigned int*>(a.max_sigma), bits);
+  }
+  if (STATS) {
+    unsigned int r = __reduce_add_sync(0xFFFFFFFFu, cnt.rays), n = __reduce_add_sync(0xFFFFFFFFu, cnt.nodes);
+    unsigned int c = __reduce_add_sync(0xFFFFFFFFu, cnt.chords), h = __reduce_add_sync(0xFFFFFFFFu, cnt.shaded);
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, (unsigned long long)r);
+      atomicAdd(a.stats + 1, (unsigned long long)n);
+      atomicAdd(a.stats + 2, (unsigned long long)c);
+      atomicAdd(a.stats + 3, (unsigned long long)h);
+    }
   }
 }
 
@@ -371,6 +396,7 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.base_dirs = s->base_dirs;
   a.hit_ids = p.hit_ids;
   a.max_sigma = p.max_sigma;
+  a.stats = p.stats;
   a.width = p.image_width;
   a.height = p.image_height;
   a.row_begin = p.row_begin;
@@ -393,10 +419,13 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;
   const size_t dyn = smem ? scene_bytes : 0;
-  if (smem && portals) k_render<true, true><<<tiles, kBlock, dyn, stream>>>(a);
-  else if (smem) k_render<true, false><<<tiles, kBlock, dyn, stream>>>(a);
-  else if (portals) k_render<false, true><<<tiles, kBlock, 0, stream>>>(a);
-  else k_render<false, false><<<tiles, kBlock, 0, stream>>>(a);
+  if (p.stats) {  // counting build
+    if (smem) k_render<true, true, true><<<tiles, kBlock, dyn, stream>>>(a);
+    else k_render<false, true, true><<<tiles, kBlock, 0, stream>>>(a);
+  } else if (smem && portals) k_render<true, true, false><<<tiles, kBlock, dyn, stream>>>(a);
+  else if (smem) k_render<true, false, false><<<tiles, kBlock, dyn, stream>>>(a);
+  else if (portals) k_render<false, true, false><<<tiles, kBlock, 0, stream>>>(a);
+  else k_render<false, false, false><<<tiles, kBlock, 0, stream>>>(a);
   RDC_CUDA(cudaGetLastError());
   return 0;
 }

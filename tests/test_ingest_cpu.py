@@ -1,0 +1,126 @@
+"""Host logic: XML loader + ingest (no GPU). Checks the product's C++ ingest against
+   (1) the reference's rapidxml element tree (golden hashes, and live when oracle/_ref exists),
+   (2) the oracle's independent Python restatement of optixHello.cpp:212-515,
+   (3) the worked example of SURVEY.md Appendix B.4."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import all_scene_files, assert_scene_equal, scene_ids, XML_DIR
+from oracle import pyoracle as po
+from raytracingdiffusioncurves_b200 import api
+
+
+@pytest.mark.parametrize("path", all_scene_files(), ids=scene_ids())
+def test_element_tree_matches_rapidxml_golden(path, golden_dir):
+    with open(os.path.join(golden_dir, "xml_dump_sha256.json")) as fh:
+        golden = json.load(fh)
+    got = hashlib.sha256(api.xml_dump(path).encode()).hexdigest()
+    assert got == golden[os.path.relpath(path, XML_DIR)]
+
+
+@pytest.mark.parametrize("path", all_scene_files()[:6], ids=scene_ids()[:6])
+def test_element_tree_matches_rapidxml_live(path):
+    if not os.path.exists(po.REF_XML_DUMP):
+        pytest.skip("oracle/_ref/ref_xml_dump not built")
+    assert api.xml_dump(path) == po.ref_xml_dump(path)
+
+
+@pytest.mark.parametrize("orzan", [True, False], ids=["orzan", "native"])
+@pytest.mark.parametrize("path", all_scene_files(), ids=scene_ids())
+def test_ingest_matches_oracle(path, orzan):
+    got = api.HostScene.from_xml_file(path, api.default_ingest_options(use_diffusion_curve_save=int(orzan))).to_numpy()
+    want = po.ingest_xml(path, orzan)
+    assert_scene_equal(got, want)
+
+
+def test_ingest_knobs_reach_the_arrays(xml_dir):
+    path = os.path.join(xml_dir, "line.xml")  # end-capped, no weight_degree_set
+    opts = api.default_ingest_options(endcap_size=12.0, default_weight_degree=0.75)
+    got = api.HostScene.from_xml_file(path, opts).to_numpy()
+    want = po.ingest_xml(path, True, default_weight_degree=0.75, endcap_size=12.0)
+    assert_scene_equal(got, want)
+    base = po.ingest_xml(path, True)
+    assert not np.array_equal(base["vertices"], want["vertices"])
+    assert np.all(want["weight_degree"][: want["n_weight_degree"]] == 0.75)
+
+
+def test_arch_known_answers(xml_dir):
+    """SURVEY.md Appendix B.4."""
+    s = api.HostScene.from_xml_file(os.path.join(xml_dir, "arch.xml")).to_numpy()
+    assert (s["image_width"], s["image_height"]) == (512, 512)
+    assert s["segment_indices"].tolist() == [0, 4, 8]
+    assert s["curve_map"].tolist() == [0, 0, 0]
+    assert s["curve_index"].tolist() == [0, 1, 2]
+    assert s["curve_map_inverse"].tolist() == [0]
+    assert s["curve_connect"].tolist() == [-1]
+    assert s["vertices"].shape == (12, 3)
+    np.testing.assert_array_equal(s["vertices"][4:8, :2], [[384, 1408], [-384, -128], [384, -128], [-384, 1408]])
+    b = s["vertices"][4:8, :2]
+    np.testing.assert_allclose((b[0] + 4 * b[1] + b[2]) / 6, [-128, 128])
+    np.testing.assert_allclose(s["color_left_u"][:9], [0, 1, 1, 1.3, 1.7, 2, 2, 2, 3], rtol=1e-6)
+    assert s["color_left_index"].tolist() == [[0, 9]] and s["color_right_index"].tolist() == [[0, 9]]
+    np.testing.assert_array_equal(s["blur_u"][:4], [0, 1, 3, 3])
+    np.testing.assert_array_equal(s["blur"][:4], 0)
+    np.testing.assert_allclose(s["weight_u"][:7], [0, 1, 1.3, 1.5, 1.7, 2, 3], rtol=1e-6)
+    np.testing.assert_array_equal(s["weight"][:7], 1)
+    np.testing.assert_array_equal(s["weight_degree_u"][:4], [0, 1, 2, 3])
+    np.testing.assert_array_equal(s["weight_degree"][:4], 0.5)
+    np.testing.assert_array_equal(s["color_left"][2], [1, 0, 0])  # R=0 G=0 B=255 stored as (B,G,R)
+    # the stop walk over-reads: every u array ends in two +INF sentinels
+    for fam in ("color_left", "color_right", "blur", "weight", "weight_degree"):
+        assert np.all(np.isinf(s[fam + "_u"][-2:]))
+    # start cap hugs the first control point
+    cap = s["vertices"][0:4, :2]
+    assert np.all(np.abs((cap[0] + 4 * cap[1] + cap[2]) / 6 - [-128, 128]) < 1e-3)
+
+
+def test_portal_demo_structure(xml_dir):
+    s = api.HostScene.from_xml_file(os.path.join(xml_dir, "PortalDemo.xml")).to_numpy()
+    assert s["curve_connect"].tolist() == [-1, -1, 3, 2, 4]
+    assert s["curve_map_inverse"].tolist() == [0, 1, 2, 3, 4]
+    assert s["weight"][s["weight_index"][1, 0]] == 0  # absorbing wall
+
+
+def test_error_behaviour(tmp_path):
+    with pytest.raises(api.RdcError) as e:
+        api.HostScene.from_xml_file(str(tmp_path / "missing.xml"))
+    assert e.value.code == -3  # RDC_E_IO
+    bad = tmp_path / "bad.xml"
+    bad.write_text("<curve_set image_width='4' image_height='4'><curve></curve_set>")
+    with pytest.raises(api.RdcError) as e:
+        api.HostScene.from_xml_file(str(bad))
+    assert e.value.code == -2  # RDC_E_PARSE
+    three = tmp_path / "three.xml"
+    three.write_text(
+        "<curve_set image_width='4' image_height='4'><curve><control_points_set>"
+        "<control_point x='0' y='0'/><control_point x='1' y='0'/><control_point x='2' y='0'/>"
+        "</control_points_set></curve></curve_set>")
+    with pytest.raises(api.RdcError) as e:
+        api.HostScene.from_xml_file(str(three))
+    assert e.value.code == -2 and "3k+1" in str(e.value)
+    empty = tmp_path / "empty.xml"
+    empty.write_text("<!DOCTYPE CurveSetXML><curve_set image_width='4' image_height='4'></curve_set>")
+    with pytest.raises(api.RdcError):
+        api.HostScene.from_xml_file(str(empty))
+
+
+def test_synthetic_scene_is_deterministic_and_loads():
+    a = api.synth_xml(200, 1024, 1024)
+    b = api.synth_xml(200, 1024, 1024)
+    assert a == b and a != api.synth_xml(200, 1024, 1024, seed=1)
+    s = api.HostScene.from_xml_text(a).to_numpy()
+    assert len(s["curve_connect"]) == 200 and len(s["segment_indices"]) == 200
+    assert s["n_weight"] == 400 and np.all(s["weight"][:400] == 1)
+
+
+def test_image_to_rgba8_follows_the_screenshot_convention():
+    img = np.zeros((2, 3, 4), np.float32)
+    img[0, 0] = [0.5, 2.0, np.nan, 1.0]
+    img[1, 2] = [1.0, 0.25, -1.0, 1.0]
+    out = api.image_to_rgba8(img, flip=False)
+    assert out[0, 0].tolist() == [127, 255, 0, 255] and out[1, 2].tolist() == [255, 63, 0, 255]
+    assert np.array_equal(api.image_to_rgba8(img, flip=True), out[::-1])

@@ -1,0 +1,236 @@
+"""Parity tests proper: the CUDA path, through the C ABI, against the CPU oracle on the same seeded rays.
+
+Bar (BASELINE.json north_star): first-hit chord index of every primary ray bit-exact, per-pixel RGB
+within 1e-4 absolute (fp32), PSNR reported. Chord tables (integer/bit work) are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GpuRenderer, bits, compare_images, copy_params
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1e-4  # absolute, fp32 — the tolerance north_star states
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from raytracingdiffusioncurves_b200 import api as _api
+
+    return _api
+
+
+def product_params(api, p):
+    return copy_params(p, api.FrameParams)
+
+
+SCENES = ["arch.xml", "arch2.xml", "line.xml", "test.xml", "test2.xml", "test3.xml", "test4.xml", "test5.xml", "circles.xml",
+          "endcap.xml", "weight_demo.xml", "PortalDemo.xml", "DiffusionCurvePack/behindthecurtain.xml",
+          "DiffusionCurvePack/dolphin.xml", "DiffusionCurvePack/drape.xml", "DiffusionCurvePack/face.xml",
+          "DiffusionCurvePack/fille.xml", "DiffusionCurvePack/lady_bug.xml", "DiffusionCurvePack/roses_spirales.xml",
+          "DiffusionCurvePack/zephyr.xml"]
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_chord_tables_bit_exact(name, xml_dir, api, port_oracle):
+    path = os.path.join(xml_dir, name)
+    r = GpuRenderer(path)
+    geom, ids = r.scene.chords()
+    ogeom, oids = port_oracle.chords(po.ingest_xml(path, True))
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(geom), bits(ogeom))
+    st = r.scene.stats
+    assert st.n_chords == len(ogeom) and st.n_nodes == max(st.n_chords - 1, 1) and st.bvh_depth <= 62
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_render_parity_small(name, xml_dir, api, port_oracle):
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    big = "Pack" in name
+    w, h, n = (40, 30, 16) if big else (64, 48, 32)
+    zoom = scene["image_height"] / h
+    p = po.make_params(w, h, n, zoom_factor=zoom)
+    oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+    r = GpuRenderer(path)
+    for traversal in (api.TRAVERSAL_LBVH, api.TRAVERSAL_BRUTE_FORCE):
+        out = r.render(product_params(api, po.make_params(w, h, n, zoom_factor=zoom, traversal=traversal)), want_hits=True)
+        assert np.array_equal(out["hits"], ohits), f"hit indices differ (traversal {traversal})"
+        d, psnr = compare_images(out["image"], oimg, RGB_TOL)
+        m = ~np.isnan(oblur)
+        assert np.array_equal(np.isnan(out["blur_map"]), np.isnan(oblur))
+        assert np.max(np.abs(out["blur_map"][m] - oblur[m]), initial=0) <= 1e-4 * max(1.0, float(np.nanmax(oblur, initial=0)))
+        print(f"{name}: max|rgb diff| {d:.2e}, psnr {psnr:.1f} dB")
+
+
+@pytest.mark.parametrize("case", ["arch", "portal", "lady_bug", "weight_demo", "drape"])
+def test_render_matches_reference_golden(case, golden_dir, xml_dir, api):
+    """Golden vectors produced by the reference's own DeviceCode.cu (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, f"render_{case}.npz"))
+    w, h, n, zoom = z["meta"]
+    r = GpuRenderer(os.path.join(xml_dir, str(z["scene_file"])))
+    out = r.render(api.default_frame_params(int(w), int(h), float(n), zoom_factor=float(zoom)), want_hits=True)
+    assert np.array_equal(out["hits"], z["hits"])
+    compare_images(out["image"], z["image"], RGB_TOL)
+
+
+@pytest.mark.parametrize("kw", [dict(use_aa=0), dict(use_diffusion_curve_save=0), dict(frame=7, seed=123),
+                                dict(offset_x=31.5, offset_y=-12.25, zoom_factor=3.0), dict(number_of_rays_per_pixel=7.5)],
+                         ids=["no_aa", "native", "frame_seed", "pan_zoom", "fractional_rpp"])
+def test_switches_and_knobs(kw, xml_dir, api, port_oracle):
+    path = os.path.join(xml_dir, "DiffusionCurvePack/lady_bug.xml")
+    orzan = kw.get("use_diffusion_curve_save", 1) != 0
+    scene = po.ingest_xml(path, orzan)
+    base = dict(zoom_factor=10.0)
+    base.update(kw)
+    n = base.pop("number_of_rays_per_pixel", 24)
+    p = po.make_params(48, 40, n, **base)
+    oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+    out = GpuRenderer(path, orzan=orzan).render(product_params(api, p), want_hits=True)
+    assert np.array_equal(out["hits"], ohits)
+    compare_images(out["image"], oimg, RGB_TOL)
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 31])
+def test_portals_iterative_retrace(depth, xml_dir, api, port_oracle):
+    """config 4: connects attribute; the CUDA loop against the oracle's recursion, up to depth 31."""
+    path = os.path.join(xml_dir, "PortalDemo.xml")
+    scene = po.ingest_xml(path, True)
+    p = po.make_params(96, 54, 32, zoom_factor=512 / 54, max_trace_depth=depth)
+    oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+    out = GpuRenderer(path).render(product_params(api, p), want_hits=True)
+    assert np.array_equal(out["hits"], ohits)
+    compare_images(out["image"], oimg, RGB_TOL)
+
+
+def test_row_bands_concatenate_bit_exactly(xml_dir, api):
+    """Partition invariance: 1-GPU image == concatenation of bands, bit for bit."""
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))
+    w, h, n = 80, 61, 16
+    full = r.render(api.default_frame_params(w, h, n, zoom_factor=512 / h), want_hits=True)
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            b, e = api.row_band(h, rank, world)
+            parts.append(r.render(api.default_frame_params(w, h, n, zoom_factor=512 / h, row_begin=b, row_end=e), want_hits=True))
+        for key in ("image", "blur_map", "hits"):
+            assert np.array_equal(bits(np.concatenate([q[key] for q in parts])), bits(full[key])), (world, key)
+
+
+def test_lbvh_equals_brute_force_at_headline_size(xml_dir, api):
+    """Size-independent property at BASELINE's config 2 (arch.xml 1920x1080, 128 rays/pixel):
+    the LBVH traversal and the no-tree kernel agree on every one of the 265 M first hits."""
+    import torch
+
+    r = GpuRenderer(os.path.join(xml_dir, "arch.xml"))
+    w, h, n = 1920, 1080, 128
+    sums = []
+    for traversal in (api.TRAVERSAL_LBVH, api.TRAVERSAL_BRUTE_FORCE):
+        acc = torch.zeros((2,), dtype=torch.int64, device="cuda")
+        imgs = []
+        for b in range(0, h, 120):  # bands keep the hit buffer at 118 MB
+            p = api.default_frame_params(w, h, n, zoom_factor=512 / h, row_begin=b, row_end=b + 120, traversal=traversal)
+            hits = torch.empty((120, w, n), dtype=torch.int32, device="cuda")
+            image = torch.empty((120, w, 4), dtype=torch.float32, device="cuda")
+            sigma = torch.empty((120, w), dtype=torch.float32, device="cuda")
+            p.hit_ids = hits.data_ptr()
+            r.scene.render(p, image.data_ptr(), sigma.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            hv = hits.to(torch.int64) & 0xFFFFFFFF
+            pos = torch.arange(hv.numel(), device="cuda", dtype=torch.int64).reshape(hv.shape) + b * w * n
+            acc[0] += hv.sum()
+            acc[1] += ((hv + 1) * (pos % 1000003)).sum()  # order-sensitive checksum
+            imgs.append(image)
+        torch.cuda.synchronize()
+        sums.append((acc.cpu().tolist(), torch.cat(imgs)))
+    assert sums[0][0] == sums[1][0]
+    assert torch.equal(sums[0][1].view(torch.int32), sums[1][1].view(torch.int32))
+
+
+@pytest.mark.parametrize("name", ["DiffusionCurvePack/face.xml", "DiffusionCurvePack/dolphin.xml", "arch.xml"])
+def test_blur_parity(name, xml_dir, api, port_oracle):
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    w, h, n = 96, 64, 8
+    p = po.make_params(w, h, n, zoom_factor=scene["image_height"] / h)
+    oimg, oblur, _ = port_oracle.render(scene, p)
+    r = GpuRenderer(path)
+    out = r.render(product_params(api, p), blur=True)
+    # blur the GPU's own render with the oracle's blur: isolates the blur kernels
+    want = port_oracle.blur(out["image"], out["blur_map"])
+    assert np.array_equal(np.isnan(out["blurred"]), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.max(np.abs(out["blurred"][m] - want[m]), initial=0) <= 1e-5
+    if name == "arch.xml":
+        assert out["max_sigma"] == 0.0 and np.array_equal(bits(out["blurred"]), bits(out["image"]))
+    else:
+        assert out["max_sigma"] > 0.0
+        again = r.render(product_params(api, p), blur=True, use_flag=False)
+        assert np.array_equal(bits(again["blurred"]), bits(out["blurred"]))
+    # end to end against the all-oracle pipeline
+    full = port_oracle.blur(oimg, oblur)
+    m = ~np.isnan(full) & ~np.isnan(out["blurred"])
+    assert np.max(np.abs(out["blurred"][m] - full[m]), initial=0) <= 2e-4
+
+
+def test_reference_named_helpers(api):
+    import torch
+
+    x = torch.empty(1000, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    api.lib.setFloatDevice(x.data_ptr(), 1000, 1e-3, s)
+    api.lib.setupCurand(None, 16, 16, s)
+    img = torch.rand((20, 30, 4), dtype=torch.float32, device="cuda")
+    sigma = torch.full((20, 30), 1.25, dtype=torch.float32, device="cuda")
+    ref = img.clone()
+    api.lib.gaussianBlur(img.data_ptr(), img.data_ptr(), sigma.data_ptr(), 30, 20, s)  # in place, as the reference calls it
+    torch.cuda.synchronize()
+    assert torch.all(x == 1e-3)
+    from oracle import pyoracle
+
+    want = pyoracle.Oracle("port").blur(ref.cpu().numpy(), sigma.cpu().numpy())
+    assert np.max(np.abs(img.cpu().numpy() - want)) <= 1e-5
+
+
+def test_frame_to_host_equals_device_path(xml_dir, api):
+    import torch
+
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/fille.xml"))
+    w, h, n = 64, 48, 8
+    p = api.default_frame_params(w, h, n, zoom_factor=512 / h)
+    dev = r.render(p, blur=True)
+    host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    p2 = api.default_frame_params(w, h, n, zoom_factor=512 / h)
+    r.scene.render_frame_to_host(p2, True, host.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(bits(host.numpy()), bits(dev["blurred"]))
+
+
+def test_bad_arguments_are_reported(xml_dir, api):
+    r = GpuRenderer(os.path.join(xml_dir, "arch.xml"))
+    import torch
+
+    img = torch.empty((8, 8, 4), device="cuda")
+    sig = torch.empty((8, 8), device="cuda")
+    for kw in (dict(max_trace_depth=32), dict(row_begin=5, row_end=5), dict(row_end=9), dict(number_of_rays_per_pixel=0.0)):
+        with pytest.raises(api.RdcError):
+            r.scene.render(api.default_frame_params(8, 8, kw.pop("number_of_rays_per_pixel", 4), **kw), img.data_ptr(), sig.data_ptr())
+
+
+def test_synthetic_scene_global_memory_path(api, port_oracle, tmp_path):
+    """A scene too large for the shared-memory staging path (config 5 in miniature)."""
+    xml = api.synth_xml(3000, 1024, 1024)
+    f = tmp_path / "synth.xml"
+    f.write_bytes(xml)
+    scene = po.ingest_xml(str(f), True)
+    p = po.make_params(48, 48, 8, zoom_factor=1024 / 48)
+    oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+    r = GpuRenderer(str(f))
+    assert r.scene.stats.traversal_bytes > 32 * 1024
+    out = r.render(product_params(api, p), want_hits=True)
+    assert np.array_equal(out["hits"], ohits)
+    compare_images(out["image"], oimg, RGB_TOL)

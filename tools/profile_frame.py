@@ -1,0 +1,42 @@
+"""Renders a few frames of a bench workload and exits — the short command ncu wraps.
+    python tools/profile_frame.py [workload] [frames]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from raytracingdiffusioncurves_b200 import api  # noqa: E402
+
+
+def main():
+    workload = sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD
+    frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    spec, width, height, rpp, depth = bench.WORKLOADS[workload]
+    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
+    kind, payload = bench.scene_source(spec)
+    host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
+    stream = torch.cuda.current_stream().cuda_stream
+    scene = api.Scene(host.arrays, None, stream)
+    image = torch.empty((height, width, 4), dtype=torch.float32, device="cuda")
+    sigma = torch.empty((height, width), dtype=torch.float32, device="cuda")
+    scratch = torch.empty_like(image)
+    flag = torch.zeros((1,), dtype=torch.float32, device="cuda")
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for f in range(frames):
+        flag.zero_()
+        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=f)
+        p.max_sigma = flag.data_ptr()
+        t0.record()
+        scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
+        api.gaussian_blur(image.data_ptr(), image.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), width, height, 0, height,
+                          flag.data_ptr(), stream)
+        t1.record()
+        torch.cuda.synchronize()
+        print(f"frame {f}: {t0.elapsed_time(t1):.3f} ms, chords {scene.stats.n_chords}, max sigma {flag.item():.3f}")
+
+
+if __name__ == "__main__":
+    main()
