@@ -46,3 +46,9 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle sass clean
+
+# kernel-tuning variants (not shipped): make variant MINB=3 -> build/librdc_b200_mb3.so
+variant:
+	@mkdir -p $(BUILD)/v$(MINB)
+	for f in $(CU_SRCS); do $(NVCC) $(NVFLAGS) -DRDC_MIN_BLOCKS=$(MINB) -c $$f -o $(BUILD)/v$(MINB)/$$(basename $$f).o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o $(BUILD)/librdc_b200_mb$(MINB).so $(BUILD)/v$(MINB)/*.o $(CPP_OBJS)

@@ -32,6 +32,8 @@ WORKLOADS = {
     "arch_1080p_128rpp": ("xml:arch.xml", 1920, 1080, 128, 2),            # BASELINE.json configs[1] (headline)
     "arch_512_128rpp": ("xml:arch.xml", 512, 512, 128, 2),                # configs[0]
     "portal_1080p_depth31": ("xml:PortalDemo.xml", 1920, 1080, 128, 31),  # configs[3]
+    "ladybug_1080p_128rpp": ("xml:DiffusionCurvePack/lady_bug.xml", 1920, 1080, 128, 2),   # dense bundled scene
+    "dolphin_4k_256rpp": ("xml:DiffusionCurvePack/dolphin.xml", 3840, 2160, 256, 2),        # configs[2], largest bundled scene
     "synth100k_8k_512rpp": ("synth:100000:8192", 8192, 8192, 512, 2),     # configs[4]
     "synth100k_2k_64rpp": ("synth:100000:8192", 2048, 2048, 64, 2),       # configs[4] geometry, smaller frame
 }
@@ -52,6 +54,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
+
+
+def workload_zoom(spec, height):
+    """zoom = xml image height / output height, without needing the product library."""
+    kind, _, rest = spec.partition(":")
+    if kind == "synth":
+        return float(rest.split(":")[1]) / height
+    import re
+
+    with open(os.path.join(XML_DIR, rest), "rb") as fh:
+        head = fh.read(4096).decode("utf-8", "replace")
+    return float(re.search(r'image_height="(\d+)"', head).group(1)) / height
 
 
 def scene_source(spec):
@@ -116,7 +130,7 @@ def cpu_oracle_run(kind_pref, scene_spec, width, height, rpp, depth, zoom, targe
     from oracle import pyoracle as po
 
     kind = kind_pref if (kind_pref == "port" or po.Oracle.reference_available()) else "port"
-    if kind == "reference" and depth != 2:
+    if kind == "reference" and depth != 2:  # noqa
         kind = "port"  # the reference build is compiled with MAX_TRACE_DEPTH 2
     oracle = po.Oracle(kind)
     skind, payload = scene_source(scene_spec)
@@ -156,7 +170,7 @@ def run_reference(args):
     if rank != 0:
         return
     spec, width, height, rpp, depth = WORKLOADS[args.workload]
-    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
+    zoom = workload_zoom(spec, height)
     per_step_seconds = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     results = []
     for i in range(args.warmup + args.steps):
@@ -203,13 +217,13 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     spec, width, height, rpp, depth = WORKLOADS[args.workload]
-    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
     kind, payload = scene_source(spec)
     t_setup = time.perf_counter()
     host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
     scene = api.Scene(host.arrays, None, stream)
     torch.cuda.synchronize()
     setup_ms = (time.perf_counter() - t_setup) * 1e3
+    zoom = float(host.arrays.image_height) / height  # the XML frame stays visible vertically
 
     row_begin, row_end = api.row_band(height, rank, world)
     rows = row_end - row_begin

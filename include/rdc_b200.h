@@ -78,10 +78,10 @@ typedef struct rdc_accel_options {
 typedef struct rdc_scene rdc_scene; /* opaque: device-resident SoA scene + chords + LBVH, one per device */
 
 typedef struct rdc_scene_info {
-  uint32_t n_segments, n_curves, n_chords, n_nodes, bvh_depth;
+  uint32_t n_segments, n_curves, n_chords, n_runs, n_nodes, bvh_depth; /* runs = tree leaves (<= 8 chords each) */
   int has_portals;
   uint64_t device_bytes;    /* everything the handle owns on the device            */
-  uint64_t traversal_bytes; /* nodes + chord geometry: what a ray touches          */
+  uint64_t traversal_bytes; /* nodes + leaf runs: what a ray touches                */
   float pad;                /* box padding actually used                           */
 } rdc_scene_info;
 

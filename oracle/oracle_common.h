@@ -61,9 +61,11 @@ struct Hit {
 };
 
 // every chord, no acceleration structure; [skip_lo,skip_hi] (inclusive chord ids) are invisible
-inline Hit closest_hit(const ChordSet& cs, float ox, float oy, float dx, float dy, uint32_t skip_lo, uint32_t skip_hi) {
+// `primary`: see rdc_inv_dd (rdc_math.h)
+inline Hit closest_hit(const ChordSet& cs, float ox, float oy, float dx, float dy, bool primary, uint32_t skip_lo,
+                       uint32_t skip_hi) {
   Hit h;
-  const float inv_dd = 1.0f / (dx * dx + dy * dy);
+  const float inv_dd = rdc_inv_dd(dx, dy, primary);
   const uint32_t n = (uint32_t)cs.chords.size();
   for (uint32_t c = 0; c < n; ++c) {
     if (c >= skip_lo && c <= skip_hi) continue;

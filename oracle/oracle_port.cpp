@@ -59,7 +59,7 @@ void colour_at(const uint32_t* index, const float* rgb, const float* us, uint32_
 Payload trace(const Ctx& c, float ox, float oy, float dx, float dy, unsigned depth, uint32_t skip_lo, uint32_t skip_hi,
               uint32_t* hit_id) {
   const rdc_scene_arrays& a = c.a;
-  Hit h = oracle::closest_hit(c.cs, ox, oy, dx, dy, skip_lo, skip_hi);
+  Hit h = oracle::closest_hit(c.cs, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi);
   if (hit_id) *hit_id = h.id;
   Payload out;
   if (!h.valid()) return out;  // miss: all zero

@@ -89,7 +89,7 @@ void optixTrace(OptixTraversableHandle, float3 o, float3 d, float, float, float,
     skip_lo = cs.seg_base[target] + (uint32_t)klo;
     skip_hi = cs.seg_base[target] + (uint32_t)khi;
   }
-  const oracle::Hit h = oracle::closest_hit(cs, o.x, o.y, d.x, d.y, skip_lo, skip_hi);
+  const oracle::Hit h = oracle::closest_hit(cs, o.x, o.y, d.x, d.y, tls.level == 0, skip_lo, skip_hi);
   if (tls.level == 0) tls.first_hit = h.id;
 
   const HitRecord saved = tls.cur;

@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdc_b200.so")
+LIB_PATH = os.environ.get("RDC_B200_LIB") or os.path.join(_HERE, "librdc_b200.so")  # override: kernel experiments
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -54,8 +54,8 @@ class AccelOptions(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [
-        ("n_segments", C.c_uint32), ("n_curves", C.c_uint32), ("n_chords", C.c_uint32), ("n_nodes", C.c_uint32),
-        ("bvh_depth", C.c_uint32), ("has_portals", C.c_int), ("device_bytes", C.c_uint64),
+        ("n_segments", C.c_uint32), ("n_curves", C.c_uint32), ("n_chords", C.c_uint32), ("n_runs", C.c_uint32),
+        ("n_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("has_portals", C.c_int), ("device_bytes", C.c_uint64),
         ("traversal_bytes", C.c_uint64), ("pad", C.c_float),
     ]
 
@@ -241,6 +241,7 @@ class SceneStats:
     n_segments: int
     n_curves: int
     n_chords: int
+    n_runs: int
     n_nodes: int
     bvh_depth: int
     has_portals: bool
@@ -259,7 +260,7 @@ class Scene:
         self._h = h
         info = SceneInfo()
         _check(_lib.rdc_scene_get_info(self._h, C.byref(info)), "rdc_scene_get_info")
-        self.stats = SceneStats(info.n_segments, info.n_curves, info.n_chords, info.n_nodes, info.bvh_depth,
+        self.stats = SceneStats(info.n_segments, info.n_curves, info.n_chords, info.n_runs, info.n_nodes, info.bvh_depth,
                                 bool(info.has_portals), info.device_bytes, info.traversal_bytes, info.pad)
 
     @property

@@ -4,11 +4,13 @@
 // optixAccelBuild over round cubic B-spline primitives (optixHello.cpp:765-830):
 //   1. every spline segment is cut into K parameter-uniform chords, K from a flatness bound
 //      (rdc_chord_count), end points evaluated with the bit-exact spline of rdc_math.h;
-//   2. chords are ordered by the 32-bit Morton code of their centre (cub radix sort);
-//   3. a binary radix tree is built over the sorted codes (Karras 2012), boxes are fitted bottom-up with
+//   2. consecutive chords of a segment are grouped into runs of up to RDC_RUN chords (RDC_RUN+1 points:
+//      shared end points are stored once); a run is the tree's leaf primitive;
+//   3. runs are ordered by the 32-bit Morton code of their box centre (cub radix sort);
+//   4. a binary radix tree is built over the sorted codes (Karras 2012), boxes are fitted bottom-up with
 //      one atomic counter per inner node, each node ends up holding both children's padded boxes.
-// The chord's ORIGINAL id (segment order, then k) is what hit parity is defined on; Morton order is only
-// a memory layout.
+// The chord's ORIGINAL id (segment order, then k) is what hit parity is defined on; runs and Morton order
+// are only a memory layout.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -109,26 +111,66 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
   return x;
 }
 
-__global__ void k_morton(const float4* geom, uint32_t n, Bounds b, uint32_t* codes, uint32_t* order) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  float4 g = geom[c];
-  float cx = 0.5f * (g.x + g.z), cy = 0.5f * (g.y + g.w);
+__global__ void k_run_counts(const uint32_t* chord_counts, uint32_t n_segments, uint32_t* run_counts) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_segments) run_counts[s] = (chord_counts[s] + RDC_RUN - 1) / RDC_RUN;
+}
+
+// one thread per run (original order): points, ids, tight box, Morton code of the box centre
+__global__ void k_emit_runs(const float4* chord_geom, const uint32_t* chord_base, const uint32_t* run_base,
+                            uint32_t n_segments, uint32_t n_runs, Bounds b, RunRecord* runs, uint4* run_ids, float4* run_box,
+                            uint32_t* codes, uint32_t* order) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  uint32_t lo = 0, hi = n_segments;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (run_base[mid] <= r) lo = mid; else hi = mid;
+  }
+  const uint32_t seg = lo;
+  const uint32_t K = chord_base[seg + 1] - chord_base[seg];
+  const uint32_t k_first = (r - run_base[seg]) * RDC_RUN;
+  const uint32_t count = min((uint32_t)RDC_RUN, K - k_first);
+  const uint32_t first = chord_base[seg] + k_first;
+  RunRecord rec;
+  float4 g = chord_geom[first];
+  float xmin = g.x, xmax = g.x, ymin = g.y, ymax = g.y;
+  rec.pts[0] = g.x;
+  rec.pts[1] = g.y;
+  float lx = g.x, ly = g.y;
+#pragma unroll
+  for (uint32_t j = 0; j < RDC_RUN; ++j) {
+    if (j < count) {
+      g = chord_geom[first + j];
+      lx = g.z;
+      ly = g.w;
+      xmin = fminf(xmin, lx); xmax = fmaxf(xmax, lx);
+      ymin = fminf(ymin, ly); ymax = fmaxf(ymax, ly);
+    }
+    rec.pts[2 * j + 2] = lx;  // unused slots repeat the last point
+    rec.pts[2 * j + 3] = ly;
+  }
+  rec.first_id = first;
+  rec.count = count;
+  runs[r] = rec;
+  run_ids[r] = make_uint4(first, seg, k_first, K);
+  run_box[r] = make_float4(xmin, ymin, xmax, ymax);
+  float cx = 0.5f * (xmin + xmax), cy = 0.5f * (ymin + ymax);
   float ex = fmaxf(b.xmax - b.xmin, 1e-20f), ey = fmaxf(b.ymax - b.ymin, 1e-20f);
   float nx = fminf(fmaxf((cx - b.xmin) / ex, 0.0f), 1.0f);
   float ny = fminf(fmaxf((cy - b.ymin) / ey, 0.0f), 1.0f);
-  uint32_t qx = (uint32_t)(nx * 65535.0f), qy = (uint32_t)(ny * 65535.0f);
-  codes[c] = spread16(qx) | (spread16(qy) << 1);
-  order[c] = c;
+  codes[r] = spread16((uint32_t)(nx * 65535.0f)) | (spread16((uint32_t)(ny * 65535.0f)) << 1);
+  order[r] = r;
 }
 
-__global__ void k_gather(const uint32_t* order, const float4* geom_in, const uint4* ids_in, uint32_t n, float4* geom,
-                         uint4* ids) {
+__global__ void k_gather_runs(const uint32_t* order, const RunRecord* runs_in, const uint4* ids_in, const float4* box_in,
+                              uint32_t n, RunRecord* runs, uint4* ids, float4* box) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t src = order[i];
-  geom[i] = geom_in[src];
+  runs[i] = runs_in[src];
   ids[i] = ids_in[src];
+  box[i] = box_in[src];
 }
 
 // length of the common prefix of the (code, position) keys i and j; -1 outside the array
@@ -168,15 +210,15 @@ __global__ void k_radix_tree(const uint32_t* codes, int n, BvhNode* nodes, int* 
   if (right < 0) leaf_parent[gamma + 1] = i; else nodes[right].parent = i;
 }
 
-__device__ __forceinline__ float4 chord_box(float4 g, float pad) {
-  return make_float4(fminf(g.x, g.z) - pad, fminf(g.y, g.w) - pad, fmaxf(g.x, g.z) + pad, fmaxf(g.y, g.w) + pad);
+__device__ __forceinline__ float4 padded(float4 b, float pad) {
+  return make_float4(b.x - pad, b.y - pad, b.z + pad, b.w + pad);
 }
 __device__ __forceinline__ float4 box_union(float4 a, float4 b) {
   return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
 // Bottom-up fit. The second thread to reach a node owns it: both children are complete by then.
-__global__ void k_fit_boxes(const float4* geom, int n, float pad, const int* leaf_parent, BvhNode* nodes,
+__global__ void k_fit_boxes(const float4* leaf_box, int n, float pad, const int* leaf_parent, BvhNode* nodes,
                             float4* node_box, unsigned int* arrivals) {
   int leaf = blockIdx.x * blockDim.x + threadIdx.x;
   if (leaf >= n) return;
@@ -186,8 +228,8 @@ __global__ void k_fit_boxes(const float4* geom, int n, float pad, const int* lea
     if (atomicAdd(&arrivals[node], 1u) == 0u) return;
     __threadfence();
     int l = nodes[node].left, r = nodes[node].right;
-    float4 lb = l < 0 ? chord_box(geom[~l], pad) : __ldcg(&node_box[l]);  // L2: written by another SM
-    float4 rb = r < 0 ? chord_box(geom[~r], pad) : __ldcg(&node_box[r]);
+    float4 lb = l < 0 ? padded(leaf_box[~l], pad) : __ldcg(&node_box[l]);  // L2: written by another SM
+    float4 rb = r < 0 ? padded(leaf_box[~r], pad) : __ldcg(&node_box[r]);
     nodes[node].lbox = lb;
     nodes[node].rbox = rb;
     node_box[node] = box_union(lb, rb);
@@ -195,9 +237,9 @@ __global__ void k_fit_boxes(const float4* geom, int n, float pad, const int* lea
   }
 }
 
-__global__ void k_single_chord_root(const float4* geom, float pad, BvhNode* nodes) {
+__global__ void k_single_leaf_root(const float4* leaf_box, float pad, BvhNode* nodes) {
   const float inf = __int_as_float(0x7f800000);
-  nodes[0].lbox = chord_box(geom[0], pad);
+  nodes[0].lbox = padded(leaf_box[0], pad);
   nodes[0].rbox = make_float4(inf, inf, -inf, -inf);  // never entered
   nodes[0].left = ~0;
   nodes[0].right = ~0;
@@ -262,6 +304,9 @@ void destroy_scene(rdc_scene* s) {
   cudaGetDevice(&prev);
   cudaSetDevice(s->device);
   for (void* p : s->allocations) cudaFree(p);
+  cudaFree(s->frame_image);
+  cudaFree(s->frame_scratch);
+  cudaFree(s->frame_sigma);
   cudaSetDevice(prev);
   delete s;
 }
@@ -360,16 +405,51 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     return fail(RDC_E_LIMIT);
   }
 
-  float4* geom_in = nullptr;
+  // chords stay in original order (hit ids, download hook); runs + tree are what rays touch
+  float4* chord_geom = up.alloc<float4>(n_chords);
+  uint4* chord_ids = up.alloc<uint4>(n_chords);
+  uint32_t* run_counts = up.alloc<uint32_t>(nseg + 1);
+  uint32_t* run_base = up.alloc<uint32_t>(nseg + 1);
+  unsigned int* max_depth = up.alloc<unsigned int>(1);
+  if (up.status) return fail(up.status);
+  const float inf = std::numeric_limits<float>::infinity();
+  Bounds init{inf, inf, -inf, -inf};
+  BUILD_CUDA(cudaMemcpyAsync(bounds, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+  k_emit_chords<<<blocks_for(n_chords), kThreads, 0, stream>>>(d.vertices, d.segment_indices, base, nseg, n_chords,
+                                                               chord_geom, chord_ids, bounds);
+  BUILD_CUDA(cudaGetLastError());
+  BUILD_CUDA(cudaMemsetAsync(run_counts, 0, (nseg + 1) * sizeof(uint32_t), stream));
+  k_run_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(counts, nseg, run_counts);
+  BUILD_CUDA(cudaGetLastError());
+  BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, run_counts, run_base, (int)(nseg + 1), stream));
+  BUILD_CUDA(cudaMalloc(&scan_temp, temp_bytes ? temp_bytes : 1));
+  scan_err = cub::DeviceScan::ExclusiveSum(scan_temp, temp_bytes, run_counts, run_base, (int)(nseg + 1), stream);
+  uint32_t n_runs = 0;
+  Bounds hb{};
+  if (scan_err == cudaSuccess) scan_err = cudaMemcpyAsync(&n_runs, run_base + nseg, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+  if (scan_err == cudaSuccess) scan_err = cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, stream);
+  if (scan_err == cudaSuccess) scan_err = cudaStreamSynchronize(stream);
+  cudaFree(scan_temp);
+  BUILD_CUDA(scan_err);
+  if (n_runs == 0 || !(std::isfinite(hb.xmin) && std::isfinite(hb.ymin) && std::isfinite(hb.xmax) && std::isfinite(hb.ymax))) {
+    set_error("accel: control points are not finite");
+    return fail(RDC_E_INVALID);
+  }
+  float extent = std::fmax(std::fmax(std::fabs(hb.xmin), std::fabs(hb.xmax)), std::fmax(std::fabs(hb.ymin), std::fabs(hb.ymax)));
+  // curve_width thickens every leaf box; the relative term keeps the padding above the rounding of the
+  // chord test (a few ulp of the largest coordinate), which is what makes culling exact.
+  const float pad = o.curve_width + 4e-6f * extent;
+
+  RunRecord* runs_in = nullptr;
   uint4* ids_in = nullptr;
+  float4 *box_in = nullptr, *leaf_box = nullptr, *node_box = nullptr;
   uint32_t *codes_in = nullptr, *codes = nullptr, *order_in = nullptr, *order = nullptr;
   void* sort_temp = nullptr;
-  float4* node_box = nullptr;
   unsigned int* arrivals = nullptr;
   int* leaf_parent = nullptr;
   auto free_temps = [&]() {
-    cudaFree(geom_in); cudaFree(ids_in); cudaFree(codes_in); cudaFree(codes); cudaFree(order_in); cudaFree(order);
-    cudaFree(sort_temp); cudaFree(node_box); cudaFree(arrivals); cudaFree(leaf_parent);
+    cudaFree(runs_in); cudaFree(ids_in); cudaFree(box_in); cudaFree(leaf_box); cudaFree(node_box); cudaFree(codes_in);
+    cudaFree(codes); cudaFree(order_in); cudaFree(order); cudaFree(sort_temp); cudaFree(arrivals); cudaFree(leaf_parent);
   };
 #define TEMP_CUDA(call)                                         \
   do {                                                          \
@@ -379,64 +459,47 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
       return fail(cuda_fail(e__, #call));                       \
     }                                                           \
   } while (0)
-  const uint32_t n_nodes = n_chords > 1 ? n_chords - 1 : 1;
-  TEMP_CUDA(cudaMalloc(&geom_in, n_chords * sizeof(float4)));
-  TEMP_CUDA(cudaMalloc(&ids_in, n_chords * sizeof(uint4)));
-  TEMP_CUDA(cudaMalloc(&codes_in, n_chords * sizeof(uint32_t)));
-  TEMP_CUDA(cudaMalloc(&codes, n_chords * sizeof(uint32_t)));
-  TEMP_CUDA(cudaMalloc(&order_in, n_chords * sizeof(uint32_t)));
-  TEMP_CUDA(cudaMalloc(&order, n_chords * sizeof(uint32_t)));
+  const uint32_t n_nodes = n_runs > 1 ? n_runs - 1 : 1;
+  TEMP_CUDA(cudaMalloc(&runs_in, n_runs * sizeof(RunRecord)));
+  TEMP_CUDA(cudaMalloc(&ids_in, n_runs * sizeof(uint4)));
+  TEMP_CUDA(cudaMalloc(&box_in, n_runs * sizeof(float4)));
+  TEMP_CUDA(cudaMalloc(&leaf_box, n_runs * sizeof(float4)));
   TEMP_CUDA(cudaMalloc(&node_box, n_nodes * sizeof(float4)));
+  TEMP_CUDA(cudaMalloc(&codes_in, n_runs * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&codes, n_runs * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&order_in, n_runs * sizeof(uint32_t)));
+  TEMP_CUDA(cudaMalloc(&order, n_runs * sizeof(uint32_t)));
   TEMP_CUDA(cudaMalloc(&arrivals, n_nodes * sizeof(unsigned int)));
-  TEMP_CUDA(cudaMalloc(&leaf_parent, n_chords * sizeof(int)));
-  float4* geom = up.alloc<float4>(n_chords);
-  uint4* ids = up.alloc<uint4>(n_chords);
+  TEMP_CUDA(cudaMalloc(&leaf_parent, n_runs * sizeof(int)));
+  RunRecord* runs = up.alloc<RunRecord>(n_runs);
+  uint4* run_ids = up.alloc<uint4>(n_runs);
   BvhNode* nodes = up.alloc<BvhNode>(n_nodes);
-  unsigned int* max_depth = up.alloc<unsigned int>(1);
   if (up.status) {
     free_temps();
     return fail(up.status);
   }
 
-  const float inf = std::numeric_limits<float>::infinity();
-  Bounds init{inf, inf, -inf, -inf};
-  TEMP_CUDA(cudaMemcpyAsync(bounds, &init, sizeof init, cudaMemcpyHostToDevice, stream));
-  k_emit_chords<<<blocks_for(n_chords), kThreads, 0, stream>>>(d.vertices, d.segment_indices, base, nseg, n_chords,
-                                                               geom_in, ids_in, bounds);
-  TEMP_CUDA(cudaGetLastError());
-  Bounds hb{};
-  TEMP_CUDA(cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, stream));
-  TEMP_CUDA(cudaStreamSynchronize(stream));
-  if (!(std::isfinite(hb.xmin) && std::isfinite(hb.ymin) && std::isfinite(hb.xmax) && std::isfinite(hb.ymax))) {
-    free_temps();
-    set_error("accel: control points are not finite");
-    return fail(RDC_E_INVALID);
-  }
-  float extent = std::fmax(std::fmax(std::fabs(hb.xmin), std::fabs(hb.xmax)), std::fmax(std::fabs(hb.ymin), std::fabs(hb.ymax)));
-  // curve_width thickens every chord's box; the relative term keeps the padding above the rounding of
-  // the chord test (a few ulp of the largest coordinate), which is what makes culling exact.
-  const float pad = o.curve_width + 4e-6f * extent;
-
-  k_morton<<<blocks_for(n_chords), kThreads, 0, stream>>>(geom_in, n_chords, hb, codes_in, order_in);
+  k_emit_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(chord_geom, base, run_base, nseg, n_runs, hb, runs_in, ids_in, box_in,
+                                                           codes_in, order_in);
   TEMP_CUDA(cudaGetLastError());
   size_t sort_bytes = 0;
-  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, codes_in, codes, order_in, order, (int)n_chords, 0, 32, stream));
+  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, codes_in, codes, order_in, order, (int)n_runs, 0, 32, stream));
   TEMP_CUDA(cudaMalloc(&sort_temp, sort_bytes ? sort_bytes : 1));
-  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, sort_bytes, codes_in, codes, order_in, order, (int)n_chords, 0, 32, stream));
-  k_gather<<<blocks_for(n_chords), kThreads, 0, stream>>>(order, geom_in, ids_in, n_chords, geom, ids);
+  TEMP_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, sort_bytes, codes_in, codes, order_in, order, (int)n_runs, 0, 32, stream));
+  k_gather_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(order, runs_in, ids_in, box_in, n_runs, runs, run_ids, leaf_box);
   TEMP_CUDA(cudaGetLastError());
 
   TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
-  if (n_chords == 1) {
-    k_single_chord_root<<<1, 1, 0, stream>>>(geom, pad, nodes);
+  if (n_runs == 1) {
+    k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_box, pad, nodes);
     TEMP_CUDA(cudaGetLastError());
   } else {
     TEMP_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
-    k_radix_tree<<<blocks_for(n_chords - 1), kThreads, 0, stream>>>(codes, (int)n_chords, nodes, leaf_parent);
+    k_radix_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>(codes, (int)n_runs, nodes, leaf_parent);
     TEMP_CUDA(cudaGetLastError());
-    k_fit_boxes<<<blocks_for(n_chords), kThreads, 0, stream>>>(geom, (int)n_chords, pad, leaf_parent, nodes, node_box, arrivals);
+    k_fit_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, (int)n_runs, pad, leaf_parent, nodes, node_box, arrivals);
     TEMP_CUDA(cudaGetLastError());
-    k_depth<<<blocks_for(n_chords), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_chords, max_depth);
+    k_depth<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_runs, max_depth);
     TEMP_CUDA(cudaGetLastError());
   }
   unsigned int depth = 0;
@@ -448,20 +511,25 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     return fail(RDC_E_LIMIT);
   }
 
-  d.chord_geom = geom;
-  d.chord_ids = ids;
+  d.chord_geom = chord_geom;
+  d.chord_ids = chord_ids;
   d.seg_chord_base = base;
   d.seg_chord_count = counts;
+  d.runs = runs;
+  d.run_ids = run_ids;
   d.nodes = nodes;
   d.n_chords = n_chords;
+  d.n_runs = n_runs;
   d.n_nodes = n_nodes;
+  d.root_box = make_float4(hb.xmin - pad, hb.ymin - pad, hb.xmax + pad, hb.ymax + pad);
   s->info.n_segments = a.n_segments;
   s->info.n_curves = a.n_curves;
   s->info.n_chords = n_chords;
+  s->info.n_runs = n_runs;
   s->info.n_nodes = n_nodes;
   s->info.bvh_depth = depth ? depth : 1;
   s->info.has_portals = portals ? 1 : 0;
-  s->info.traversal_bytes = (uint64_t)n_nodes * sizeof(BvhNode) + (uint64_t)n_chords * sizeof(float4);
+  s->info.traversal_bytes = (uint64_t)n_nodes * sizeof(BvhNode) + (uint64_t)n_runs * sizeof(RunRecord);
   s->info.pad = pad;
   *out = s;
   return 0;
@@ -471,18 +539,15 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
 
 int download_chords(const rdc_scene* s, float* geom, uint32_t* ids) {
   const uint32_t n = s->dev.n_chords;
-  std::vector<float4> g(n);
   std::vector<uint4> id(n);
-  RDC_CUDA(cudaMemcpy(g.data(), s->dev.chord_geom, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  RDC_CUDA(cudaMemcpy(geom, s->dev.chord_geom, n * sizeof(float4), cudaMemcpyDeviceToHost));
   RDC_CUDA(cudaMemcpy(id.data(), s->dev.chord_ids, n * sizeof(uint4), cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < n; ++i) {
-    uint32_t c = id[i].x;
-    if (c >= n) {
+    if (id[i].x != i) {
       set_error("chord table is corrupt");
       return RDC_E_INVALID;
     }
-    geom[4 * c + 0] = g[i].x; geom[4 * c + 1] = g[i].y; geom[4 * c + 2] = g[i].z; geom[4 * c + 3] = g[i].w;
-    ids[3 * c + 0] = id[i].y; ids[3 * c + 1] = id[i].z; ids[3 * c + 2] = id[i].w;
+    ids[3 * i + 0] = id[i].y; ids[3 * i + 1] = id[i].z; ids[3 * i + 2] = id[i].w;
   }
   return 0;
 }

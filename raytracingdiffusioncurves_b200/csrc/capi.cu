@@ -247,31 +247,34 @@ int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, i
     }
     const size_t rows = params->row_end - params->row_begin;
     const size_t n = rows * params->image_width;
-    float4 *image = nullptr, *scratch = nullptr;
-    float* sigma = nullptr;
-    float* flag = nullptr;
-    RDC_CUDA(cudaMallocAsync((void**)&image, n * sizeof(float4), st));
-    RDC_CUDA(cudaMallocAsync((void**)&sigma, n * sizeof(float) + sizeof(float), st));
+    if (n > scene->frame_pixels) {  // grow-only frame buffers owned by the handle
+      RDC_CUDA(cudaStreamSynchronize(st));
+      cudaFree(scene->frame_image);
+      cudaFree(scene->frame_scratch);
+      cudaFree(scene->frame_sigma);
+      scene->frame_image = scene->frame_scratch = nullptr;
+      scene->frame_sigma = nullptr;
+      scene->frame_pixels = 0;
+      RDC_CUDA(cudaMalloc((void**)&scene->frame_image, n * sizeof(float4)));
+      RDC_CUDA(cudaMalloc((void**)&scene->frame_scratch, n * sizeof(float4)));
+      RDC_CUDA(cudaMalloc((void**)&scene->frame_sigma, (n + 1) * sizeof(float)));
+      scene->frame_pixels = n;
+    }
+    float4* image = scene->frame_image;
+    float* sigma = scene->frame_sigma;
+    float* flag = sigma + scene->frame_pixels;
     rdc_frame_params p = *params;
     if (use_blur) {
-      RDC_CUDA(cudaMallocAsync((void**)&scratch, n * sizeof(float4), st));
-      flag = sigma + n;
       RDC_CUDA(cudaMemsetAsync(flag, 0, sizeof(float), st));
       p.max_sigma = flag;
     }
     int rc = rdc::render(scene, p, image, sigma, st);
     if (rc == 0 && use_blur)
-      rc = rdc::gaussian_blur(image, image, sigma, scratch, (int)params->image_width, (int)rows, 0, (int)rows, flag, st);
-    if (rc == 0) {
-      cudaError_t e = cudaMemcpyAsync(host_image, image, n * sizeof(float4), cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) rc = rdc::cuda_fail(e, "cudaMemcpyAsync(D2H image)");
-    }
-    cudaFreeAsync(image, st);
-    cudaFreeAsync(sigma, st);
-    if (scratch) cudaFreeAsync(scratch, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (rc == 0 && e != cudaSuccess) rc = rdc::cuda_fail(e, "cudaStreamSynchronize");
-    return rc;
+      rc = rdc::gaussian_blur(image, image, sigma, scene->frame_scratch, (int)params->image_width, (int)rows, 0, (int)rows, flag, st);
+    if (rc != 0) return rc;
+    RDC_CUDA(cudaMemcpyAsync(host_image, image, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    RDC_CUDA(cudaStreamSynchronize(st));
+    return 0;
   });
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/rdc_b200.h"
+#include "rdc_math.h"
 
 // One LBVH node, 48 bytes = three 128-bit loads. A node stores the padded boxes of BOTH children, so a
 // ray decides which children to visit from one node fetch. child >= 0: inner node index; child < 0:
@@ -20,6 +21,15 @@ struct __align__(16) BvhNode {
   int parent;  // -1 for the root
   int pad;
 };
+
+// Leaf primitive: up to RDC_RUN consecutive chords of one spline segment = RDC_RUN+1 points, 80 bytes =
+// five 128-bit loads. Chord j of the run joins points j and j+1; its original id is first_id + j.
+struct __align__(16) RunRecord {
+  float pts[2 * (RDC_RUN + 1)];
+  uint32_t first_id;
+  uint32_t count;
+};
+static_assert(sizeof(RunRecord) == 80, "RunRecord must be five float4");
 
 struct DevStops {
   const uint2* index;  // {start,count} per curve
@@ -38,13 +48,17 @@ struct DevScene {
   const int32_t* curve_connect;
   const uint32_t* curve_map_inverse;
   DevStops color_left, color_right, blur, weight, weight_degree;
-  // acceleration structure
-  const float4* chord_geom;        // [n_chords] Morton order: ax, ay, bx, by
-  const uint4* chord_ids;          // [n_chords] Morton order: original chord id, segment, k, K
-  const uint32_t* seg_chord_base;  // [n_segments+1] original id of chord 0 of each segment
+  // chords, original order (segment by segment, k ascending): parity ids, download hook
+  const float4* chord_geom;        // [n_chords] ax, ay, bx, by
+  const uint4* chord_ids;          // [n_chords] chord id, segment, k, K
+  const uint32_t* seg_chord_base;  // [n_segments+1] id of chord 0 of each segment
   const uint32_t* seg_chord_count; // [n_segments]   K
-  const BvhNode* nodes;            // [max(n_chords-1,1)]
-  uint32_t n_segments, n_curves, n_chords, n_nodes;
+  // acceleration structure: what rays touch
+  const RunRecord* runs;           // [n_runs] Morton order
+  const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K
+  const BvhNode* nodes;            // [max(n_runs-1,1)]
+  float4 root_box;                 // padded box of the whole scene (per-pixel angular culling)
+  uint32_t n_segments, n_curves, n_chords, n_runs, n_nodes;
 };
 
 struct rdc_scene {
@@ -57,6 +71,11 @@ struct rdc_scene {
   float base_dirs_n = -1.0f;
   uint32_t base_dirs_capacity = 0;
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
+  // frame buffers of rdc_render_frame_to_host, grown on demand and kept (no per-frame allocation)
+  float4* frame_image = nullptr;
+  float4* frame_scratch = nullptr;
+  float* frame_sigma = nullptr;  // pixels + 1: the extra float is the max-sigma flag
+  size_t frame_pixels = 0;
 };
 
 namespace rdc {

@@ -177,14 +177,14 @@ RDC_HD float rdc_hit_u(int k, int K, float s) { return ((float)k + s) / (float)K
 // computed from identical inputs, so a polyline is watertight. s is the fraction along the chord, t the
 // ray parameter of the hit point (projection form: stays accurate for grazing rays, and the hit point
 // always lies inside the chord's bounding box, which is what makes BVH culling exact).
-// inv_dd = 1/(D.D).
+// inv_dd = rdc_inv_dd(D, primary).
 // ------------------------------------------------------------------------------------------------
-RDC_HD bool rdc_ray_chord(float ox, float oy, float dx, float dy, float inv_dd, float ax, float ay, float bx,
-                          float by, float* t, float* s) {
-  float wax = ax - ox, way = ay - oy;
-  float wbx = bx - ox, wby = by - oy;
-  float ea = rdc_fma(dx, way, -(dy * wax));
-  float eb = rdc_fma(dx, wby, -(dy * wbx));
+// edge value of a chord end point P seen from the ray: cross(D, P-O), with w = P-O
+RDC_HD float rdc_edge(float dx, float dy, float wx, float wy) { return rdc_fma(dx, wy, -(dy * wx)); }
+
+// second half of the test, given both end points relative to the origin and their edge values
+RDC_HD bool rdc_chord_hit(float dx, float dy, float inv_dd, float wax, float way, float wbx, float wby, float ea,
+                          float eb, float* t, float* s) {
   if ((ea > 0.0f) == (eb > 0.0f)) return false;
   float sv = ea / (ea - eb);
   sv = fminf(fmaxf(sv, 0.0f), 1.0f);
@@ -195,6 +195,23 @@ RDC_HD bool rdc_ray_chord(float ox, float oy, float dx, float dy, float inv_dd, 
   *t = tt; *s = sv;
   return true;
 }
+
+RDC_HD bool rdc_ray_chord(float ox, float oy, float dx, float dy, float inv_dd, float ax, float ay, float bx,
+                          float by, float* t, float* s) {
+  float wax = ax - ox, way = ay - oy;
+  float wbx = bx - ox, wby = by - oy;
+  return rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, rdc_edge(dx, dy, wax, way), rdc_edge(dx, dy, wbx, wby), t, s);
+}
+
+// 1/(D.D) as used by the chord test. Primary rays are (1,0) rotated, i.e. unit length up to ~1e-6, and
+// their t is reported in units of |D|^2 like the ray parameter OptiX reports is in units of |D|: the
+// factor is exactly 1 for them (no division on the hot path). Portal continuation rays are not unit
+// length (DeviceCode.cu:243,255-256) and get the true reciprocal.
+RDC_HD float rdc_inv_dd(float dx, float dy, bool primary) { return primary ? 1.0f : 1.0f / (dx * dx + dy * dy); }
+
+// chords per leaf of the product's tree: a leaf is a run of up to RDC_RUN consecutive chords of one
+// segment (RDC_RUN+1 points), so shared end points are stored and evaluated once
+#define RDC_RUN 8
 
 // Portal continuation rays start ON the target segment (at the true spline point, DeviceCode.cu:229),
 // which lies within the flatness tolerance of chord k0 = floor(u K) of that segment. Like a ray that

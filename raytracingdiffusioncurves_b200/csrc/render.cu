@@ -2,12 +2,18 @@
 //
 // Replaces optixLaunch(...) of DeviceCode.cu's three programs (optixHello.cpp:1184):
 //   __raygen__rg      DeviceCode.cu:85-182   -> k_render's pixel loop
-//   __closesthit__ch  DeviceCode.cu:194-342  -> shade_hit (terminal :328-340, portal :220-320 as an
+//   __closesthit__ch  DeviceCode.cu:194-342  -> trace_ray (terminal :328-340, portal :220-320 as an
 //                                               iterative re-trace loop, shape of DeviceCodeIt.cu:151-170)
 //   __miss__ms        DeviceCode.cu:185-192  -> zero contribution
 //   RT-core traversal + built-in curve intersector (closed) -> closest_chord over the LBVH of accel.cu
 // Compiled with -fmad=false: plain expressions keep the reference's operation order and rounding; fused
 // operations appear only through rdc_fma (rdc_math.h).
+//
+// Work that cannot change the result is skipped, never approximated:
+//   * a ray whose angular stratum cannot reach the scene's box from anywhere inside its pixel is a miss
+//     (contributes zero, DeviceCode.cu:185-192) and is not generated at all (pixel_cull);
+//   * tree culling only uses conservative box tests; the accepted hit is the lexicographic minimum of
+//     (t, chord id) over all chords, the same rule the brute-force oracle applies.
 #include <cstdio>
 
 #include "device_scene.h"
@@ -19,7 +25,8 @@ namespace {
 constexpr int kTileW = 16, kTileH = 16, kBlock = kTileW * kTileH;
 constexpr int kStack = 64;
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
-constexpr size_t kSmemSceneLimit = 32 * 1024;  // stage nodes + chords in shared memory below this
+constexpr size_t kSmemSceneLimit = 40 * 1024;  // stage nodes + runs in shared memory below this
+constexpr int kRunVec = sizeof(RunRecord) / 16;
 
 struct RenderArgs {
   DevScene sc;
@@ -31,23 +38,24 @@ struct RenderArgs {
   unsigned long long* stats;
   uint32_t width, height, row_begin, row_end;
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
+  float n_rays;       // number_of_rays_per_pixel
   float two_over_n;   // 2 / number_of_rays_per_pixel  (DeviceCode.cu:99,120)
   float zoom, off_x, off_y;
   uint32_t frame, seed;
-  int orzan, use_aa, max_depth, brute;
+  int orzan, use_aa, max_depth, brute, cull;
 };
 
 struct Hit {
   float t, s;
-  int leaf;      // position in Morton order, -1 = miss
+  int leaf;      // run position in Morton order, -1 = miss
+  int j;         // chord inside the run
   uint32_t id;   // original chord id (tie-break, parity)
 };
 
 struct Accel {
   const BvhNode* nodes;
-  const float4* geom;
-  const uint4* ids;
-  uint32_t n_chords;
+  const float4* runs;  // kRunVec float4 per run
+  uint32_t n_runs;
 };
 
 // per-thread work counters of the counting build (rdc_frame_params::stats)
@@ -61,17 +69,42 @@ __device__ __forceinline__ float4 load16(const float4* p) {
   return __ldg(p);
 }
 
+// reciprocal for the slab test only (never decides a hit): one MUFU, |d| kept away from 0
+__device__ __forceinline__ float slab_rcp(float d) {
+  float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+  return __frcp_rn(a);
+}
+
+// All chords of one run against the ray. Edge values of the shared end points are computed once.
 template <bool SMEM, bool PORTALS>
-__device__ __forceinline__ void test_chord(const Accel& ac, int leaf, float ox, float oy, float dx, float dy,
-                                           float inv_dd, uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
-  float4 g = load16<SMEM>(ac.geom + leaf);
-  float t, s;
-  if (!rdc_ray_chord(ox, oy, dx, dy, inv_dd, g.x, g.y, g.z, g.w, &t, &s)) return;
-  if (t > h.t) return;
-  uint32_t id = __ldg(&ac.ids[leaf].x);
-  if (PORTALS && id >= skip_lo && id <= skip_hi) return;
-  if (rdc_hit_closer(t, id, h.t, h.id)) {
-    h.t = t; h.s = s; h.leaf = leaf; h.id = id;
+__device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
+                                         uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
+  const float4* rp = ac.runs + (size_t)leaf * kRunVec;
+  float p[4 * kRunVec];
+#pragma unroll
+  for (int v = 0; v < kRunVec; ++v) {
+    float4 q = load16<SMEM>(rp + v);
+    p[4 * v] = q.x; p[4 * v + 1] = q.y; p[4 * v + 2] = q.z; p[4 * v + 3] = q.w;
+  }
+  const uint32_t first_id = __float_as_uint(p[2 * (RDC_RUN + 1)]);
+  const int count = (int)__float_as_uint(p[2 * (RDC_RUN + 1) + 1]);
+  float wax = p[0] - ox, way = p[1] - oy;
+  float ea = rdc_edge(dx, dy, wax, way);
+#pragma unroll
+  for (int j = 0; j < RDC_RUN; ++j) {
+    // unused slots repeat the last point: their edge values are equal, never a sign change
+    float wbx = p[2 * j + 2] - ox, wby = p[2 * j + 3] - oy;
+    float eb = rdc_edge(dx, dy, wbx, wby);
+    if (j < count && (ea > 0.0f) != (eb > 0.0f)) {
+      float t, s;
+      if (rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, ea, eb, &t, &s)) {
+        const uint32_t id = first_id + (uint32_t)j;
+        if (!(PORTALS && id >= skip_lo && id <= skip_hi) && rdc_hit_closer(t, id, h.t, h.id)) {
+          h.t = t; h.s = s; h.leaf = leaf; h.j = j; h.id = id;
+        }
+      }
+    }
+    wax = wbx; way = wby; ea = eb;
   }
 }
 
@@ -80,20 +113,21 @@ __device__ __forceinline__ void test_chord(const Accel& ac, int leaf, float ox, 
 // hit so far (with RDC_CULL_SLACK). Leaves are tested as soon as their box is hit.
 template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
-                                             uint32_t skip_lo, uint32_t skip_hi, Counters& cnt) {
+                                             bool primary, uint32_t skip_lo, uint32_t skip_hi, Counters& cnt) {
   Hit h;
   if (STATS) cnt.rays++;
   h.t = __int_as_float(0x7f800000);
   h.s = 0.0f;
   h.leaf = -1;
+  h.j = 0;
   h.id = kMiss;
-  const float inv_dd = 1.0f / (dx * dx + dy * dy);
+  const float inv_dd = PORTALS ? rdc_inv_dd(dx, dy, primary) : 1.0f;
   if (brute) {
-    for (uint32_t c = 0; c < ac.n_chords; ++c) test_chord<SMEM, PORTALS>(ac, (int)c, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
-    if (STATS) cnt.chords += ac.n_chords;
+    for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+    if (STATS) cnt.chords += ac.n_runs * RDC_RUN;
     return h;
   }
-  const float idx = rdc_safe_inv(dx), idy = rdc_safe_inv(dy);
+  const float idx = slab_rcp(dx), idy = slab_rcp(dy);
   int stack[kStack];
   int sp = 0;
   int node = 0;
@@ -110,15 +144,15 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
     bool hl = ln <= le && ln <= lim;
     bool hr = rn <= re && rn <= lim;
     if (hl && left < 0) {
-      if (STATS) cnt.chords++;
-      test_chord<SMEM, PORTALS>(ac, ~left, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      if (STATS) cnt.chords += RDC_RUN;
+      test_run<SMEM, PORTALS>(ac, ~left, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
       hl = false;
     }
     if (hr && right < 0) {
       // the left leaf may just have shortened the ray
       if (rn <= h.t * RDC_CULL_SLACK) {
-        if (STATS) cnt.chords++;
-        test_chord<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+        if (STATS) cnt.chords += RDC_RUN;
+        test_run<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
       }
       hr = false;
     }
@@ -183,13 +217,13 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
   uint32_t skip_lo = 1, skip_hi = 0;  // empty range
   first_hit = kMiss;
   for (;;) {
-    Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, skip_lo, skip_hi, cnt);
+    Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi, cnt);
     if (depth == 0) first_hit = h.id;
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
     if (STATS) cnt.shaded++;
-    uint4 id = __ldg(ac.ids + h.leaf);
+    const uint4 id = __ldg(sc.run_ids + h.leaf);  // first chord id, segment, k of the first chord, K
     const uint32_t seg = id.y;
-    const float u = rdc_hit_u((int)id.z, (int)id.w, h.s);
+    const float u = rdc_hit_u((int)id.z + h.j, (int)id.w, h.s);
     const uint32_t curve = __ldg(sc.curve_map + seg);
     const uint32_t ordinal = __ldg(sc.curve_index + seg);
     const float cu = u + ordinal;
@@ -268,24 +302,68 @@ __global__ void k_base_dirs(float2* out, int n_iter, float two_over_n) {
   }
 }
 
+// Which rays of this pixel can reach the scene at all? Ray i leaves a point of the pixel's jitter square
+// [bx,bx+zoom]x[by,by+zoom] in a direction whose angle lies in stratum (i, i+1]*2pi/N (base direction i
+// plus a jitter of at most one stratum). Seen from any point of the square, the scene's padded box lies
+// inside the angular interval [lo,hi] computed here from the box enlarged by the square (Minkowski sum).
+// Returns false when no culling applies (origin inside the box, fractional N, interval covers everything);
+// otherwise ray i can only hit if ((i - first) mod N) <= span.
+__device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float by, int& first, int& span) {
+  const int n = a.n_iter;
+  if (!a.cull || (float)n != a.n_rays || n < 8) return false;
+  const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
+  // rounding of the subtractions below and of the origin itself: a few ulp of the magnitudes involved
+  const float mag = fabsf(bx) + fabsf(by) + jit + fabsf(a.sc.root_box.x) + fabsf(a.sc.root_box.y) + fabsf(a.sc.root_box.z) +
+                    fabsf(a.sc.root_box.w);
+  const float m = 4e-6f * mag + 1e-6f;
+  const float x0 = a.sc.root_box.x - (bx + jit) - m, x1 = a.sc.root_box.z - (bx - jit) + m;
+  const float y0 = a.sc.root_box.y - (by + jit) - m, y1 = a.sc.root_box.w - (by - jit) + m;
+  if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return false;  // the pixel may lie inside the box
+  const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
+  float dmin = 0.0f, dmax = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float px = (c & 1) ? x1 : x0, py = (c & 2) ? y1 : y0;
+    const float d = atan2f(cx * py - cy * px, cx * px + cy * py);  // signed angle from the centre direction
+    dmin = fminf(dmin, d);
+    dmax = fmaxf(dmax, d);
+  }
+  const float centre = atan2f(cy, cx);
+  const float strata_per_rad = (float)n * 0.15915494309189535f;
+  // safety: half a stratum plus the drift of the iterated rotation (n steps of ~1e-7 rad, in strata)
+  const float safety = 0.5f + 4e-8f * (float)n * (float)n;
+  const float lo = (centre + dmin) * strata_per_rad - 1.0f - safety;  // ray i reaches up to stratum end i+1
+  const float hi = (centre + dmax) * strata_per_rad + safety;
+  const int ilo = (int)floorf(lo), ihi = (int)ceilf(hi);
+  span = ihi - ilo;
+  if (span >= n - 1) return false;
+  first = ilo % n;
+  if (first < 0) first += n;
+  return true;
+}
+
+#ifndef RDC_MIN_BLOCKS
+#define RDC_MIN_BLOCKS 4  // resident blocks per SM the register allocation aims for
+#endif
+
 template <bool SMEM, bool PORTALS, bool STATS>
-__global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
+__global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderArgs a) {
   extern __shared__ uint4 smem[];
   Accel ac;
-  ac.ids = a.sc.chord_ids;
-  ac.n_chords = a.sc.n_chords;
+  ac.n_runs = a.sc.n_runs;
   if (SMEM) {
     const uint32_t node_words = a.sc.n_nodes * (uint32_t)(sizeof(BvhNode) / 16);
+    const uint32_t run_words = a.sc.n_runs * (uint32_t)kRunVec;
     const uint4* gn = reinterpret_cast<const uint4*>(a.sc.nodes);
-    const uint4* gg = reinterpret_cast<const uint4*>(a.sc.chord_geom);
+    const uint4* gr = reinterpret_cast<const uint4*>(a.sc.runs);
     for (uint32_t i = threadIdx.x; i < node_words; i += kBlock) smem[i] = __ldg(gn + i);
-    for (uint32_t i = threadIdx.x; i < a.sc.n_chords; i += kBlock) smem[node_words + i] = __ldg(gg + i);
+    for (uint32_t i = threadIdx.x; i < run_words; i += kBlock) smem[node_words + i] = __ldg(gr + i);
     __syncthreads();
     ac.nodes = reinterpret_cast<const BvhNode*>(smem);
-    ac.geom = reinterpret_cast<const float4*>(smem + node_words);
+    ac.runs = reinterpret_cast<const float4*>(smem + node_words);
   } else {
     ac.nodes = a.sc.nodes;
-    ac.geom = a.sc.chord_geom;
+    ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
   }
 
   // 16x16 pixel tile per block, 8x4 pixels per warp
@@ -306,15 +384,29 @@ __global__ void __launch_bounds__(kBlock) k_render(const RenderArgs a) {
                                  : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
     const uint32_t pixel = iy * a.width + ix;  // global pixel index: band-independent random numbers
     const size_t local_pixel = (size_t)ly * a.width + ix;
+    int cull_first = 0, cull_span = 0;
+    const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
+    // N >= 8 keeps the jitter angle within the polynomial's range: no range reduction (bit-identical)
+    const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
     for (int i = 0; i < a.n_iter; ++i) {
+      if (culling) {
+        int rel = i - cull_first;
+        if (rel < 0) rel += a.n_iter;
+        if (rel > cull_span) {  // cannot reach the scene: a miss, adds nothing
+          if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
+          continue;
+        }
+      }
       const float2 base = __ldg(a.base_dirs + i);
       // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
       const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
       float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
       if (a.use_aa) {
         float js, jc;
-        rdc_sincospi(a.two_over_n * rdc_u01(rnd.x), &js, &jc);
+        const float ang = a.two_over_n * rdc_u01(rnd.x);
+        if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
+        else rdc_sincospi(ang, &js, &jc);
         dx = base.x * jc - base.y * js;
         dy = base.x * js + base.y * jc;
         ox = base_x + rdc_u01(rnd.y) * a.zoom;
@@ -402,6 +494,7 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.row_begin = p.row_begin;
   a.row_end = p.row_end;
   a.n_iter = n_iter;
+  a.n_rays = p.number_of_rays_per_pixel;
   a.two_over_n = 2 / p.number_of_rays_per_pixel;
   a.zoom = p.zoom_factor;
   a.off_x = p.offset_x;
@@ -412,10 +505,11 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.use_aa = p.use_aa;
   a.max_depth = p.max_trace_depth;
   a.brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
+  a.cull = p.traversal == RDC_TRAVERSAL_LBVH;  // the brute-force kernel really tests every ray against every chord
 
   const uint32_t rows = p.row_end - p.row_begin;
   const uint32_t tiles = ((p.image_width + kTileW - 1) / kTileW) * ((rows + kTileH - 1) / kTileH);
-  const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_chords * sizeof(float4);
+  const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;
   const size_t dyn = smem ? scene_bytes : 0;

@@ -15,7 +15,7 @@ def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     spec, width, height, rpp, depth = bench.WORKLOADS[workload]
-    zoom = 512.0 / height if spec.startswith("xml:") else 8192.0 / height
+    zoom = bench.workload_zoom(spec, height)
     kind, payload = bench.scene_source(spec)
     host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
     stream = torch.cuda.current_stream().cuda_stream
