@@ -46,7 +46,8 @@ def test_chord_tables_bit_exact(name, xml_dir, api, port_oracle):
     assert np.array_equal(ids, oids)
     assert np.array_equal(bits(geom), bits(ogeom))
     st = r.scene.stats
-    assert st.n_chords == len(ogeom) and st.n_nodes == max(st.n_chords - 1, 1) and st.bvh_depth <= 62
+    assert st.n_chords == len(ogeom) and st.n_nodes == max(st.n_runs - 1, 1) and st.bvh_depth <= 62
+    assert -(-st.n_chords // 8) <= st.n_runs <= st.n_chords
 
 
 @pytest.mark.parametrize("name", SCENES)
