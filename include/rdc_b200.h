@@ -73,6 +73,7 @@ typedef struct rdc_accel_options {
   float curve_width;         /* optixHello.cpp:95 (1e-3): pads chord boxes                          */
   float flatness_tolerance;  /* max |curve - chord| in XML pixels; chords per segment follow from it */
   int max_chords_per_segment;
+  int run_length;            /* chords per tree leaf, 1..8; 0 = choose from the scene's density        */
 } rdc_accel_options;
 
 typedef struct rdc_scene rdc_scene; /* opaque: device-resident SoA scene + chords + LBVH, one per device */

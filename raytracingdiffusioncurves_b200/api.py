@@ -49,7 +49,8 @@ class SceneArrays(C.Structure):
 
 
 class AccelOptions(C.Structure):
-    _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int)]
+    _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int),
+                ("run_length", C.c_int)]
 
 
 class SceneInfo(C.Structure):

@@ -111,15 +111,15 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
   return x;
 }
 
-__global__ void k_run_counts(const uint32_t* chord_counts, uint32_t n_segments, uint32_t* run_counts) {
+__global__ void k_run_counts(const uint32_t* chord_counts, uint32_t n_segments, uint32_t run_len, uint32_t* run_counts) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n_segments) run_counts[s] = (chord_counts[s] + RDC_RUN - 1) / RDC_RUN;
+  if (s < n_segments) run_counts[s] = (chord_counts[s] + run_len - 1) / run_len;
 }
 
 // one thread per run (original order): points, ids, tight box, Morton code of the box centre
 __global__ void k_emit_runs(const float4* chord_geom, const uint32_t* chord_base, const uint32_t* run_base,
-                            uint32_t n_segments, uint32_t n_runs, Bounds b, RunRecord* runs, uint4* run_ids, float4* run_box,
-                            uint32_t* codes, uint32_t* order) {
+                            uint32_t n_segments, uint32_t n_runs, uint32_t run_len, Bounds b, RunRecord* runs, uint4* run_ids,
+                            float4* run_box, uint32_t* codes, uint32_t* order) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_runs) return;
   uint32_t lo = 0, hi = n_segments;
@@ -129,8 +129,8 @@ __global__ void k_emit_runs(const float4* chord_geom, const uint32_t* chord_base
   }
   const uint32_t seg = lo;
   const uint32_t K = chord_base[seg + 1] - chord_base[seg];
-  const uint32_t k_first = (r - run_base[seg]) * RDC_RUN;
-  const uint32_t count = min((uint32_t)RDC_RUN, K - k_first);
+  const uint32_t k_first = (r - run_base[seg]) * run_len;
+  const uint32_t count = min(run_len, K - k_first);
   const uint32_t first = chord_base[seg] + k_first;
   RunRecord rec;
   float4 g = chord_geom[first];
@@ -316,7 +316,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     set_error("accel: empty scene");
     return RDC_E_INVALID;
   }
-  if (!(o.flatness_tolerance > 0.0f) || o.max_chords_per_segment < 1 || !(o.curve_width >= 0.0f)) {
+  if (!(o.flatness_tolerance > 0.0f) || o.max_chords_per_segment < 1 || !(o.curve_width >= 0.0f) || o.run_length < 0 ||
+      o.run_length > RDC_RUN) {
     set_error("accel: bad options");
     return RDC_E_INVALID;
   }
@@ -325,6 +326,21 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
       set_error("accel: segment %u does not address four aligned control points", i);
       return RDC_E_INVALID;
     }
+  {
+    const uint32_t* idx[5] = {a.color_left_index, a.color_right_index, a.blur_index, a.weight_index, a.weight_degree_index};
+    const uint32_t cnt[5] = {a.n_color_left, a.n_color_right, a.n_blur, a.n_weight, a.n_weight_degree};
+    for (int f = 0; f < 5; ++f)
+      for (uint32_t c = 0; c < a.n_curves; ++c)
+        if ((uint64_t)idx[f][2 * c] + idx[f][2 * c + 1] > cnt[f]) {
+          set_error("accel: stop list %d of curve %u runs past its array", f, c);
+          return RDC_E_INVALID;
+        }
+    for (uint32_t c = 0; c < a.n_curves; ++c)
+      if (a.curve_connect[c] >= (int32_t)a.n_curves) {
+        set_error("accel: curve %u connects to a missing curve", c);
+        return RDC_E_INVALID;
+      }
+  }
   rdc_scene* s = new rdc_scene();
   cudaGetDevice(&s->device);
   Uploader up{s, stream};
@@ -367,6 +383,33 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   d.weight_degree = scalars(a.weight_degree_index, a.weight_degree, a.weight_degree_u, a.n_weight_degree);
   d.n_segments = a.n_segments;
   d.n_curves = a.n_curves;
+  {
+    std::vector<SegWalk> walk(a.n_segments);
+    for (uint32_t sg = 0; sg < a.n_segments; ++sg) {
+      const uint32_t c = a.curve_map[sg];
+      if (c >= a.n_curves) {
+        set_error("accel: segment %u maps to a missing curve", sg);
+        destroy_scene(s);
+        return RDC_E_INVALID;
+      }
+      const float u_min = (float)a.curve_index[sg];
+      SegWalk w{};
+      auto range = [&](const uint32_t* index, const float* us, uint32_t& first, uint32_t& end) {
+        first = rdc_walk_hint(index[2 * c], index[2 * c + 1], u_min, us);
+        end = index[2 * c] + index[2 * c + 1];
+      };
+      range(a.color_left_index, a.color_left_u, w.left_first, w.left_end);
+      range(a.color_right_index, a.color_right_u, w.right_first, w.right_end);
+      range(a.blur_index, a.blur_u, w.blur_first, w.blur_end);
+      range(a.weight_index, a.weight_u, w.weight_first, w.weight_end);
+      range(a.weight_degree_index, a.weight_degree_u, w.degree_first, w.degree_end);
+      range(a.color_right_index, a.color_left_u, w.portal_left_first, w.portal_left_end);
+      w.curve = c;
+      w.ordinal = a.curve_index[sg];
+      walk[sg] = w;
+    }
+    d.seg_walk = up.upload(walk.data(), walk.size());
+  }
 
   // ---- chords ------------------------------------------------------------------------------------
   const uint32_t nseg = a.n_segments;
@@ -419,7 +462,12 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
                                                                chord_geom, chord_ids, bounds);
   BUILD_CUDA(cudaGetLastError());
   BUILD_CUDA(cudaMemsetAsync(run_counts, 0, (nseg + 1) * sizeof(uint32_t), stream));
-  k_run_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(counts, nseg, run_counts);
+  // Leaf size: long runs make a shallow tree (good when curves are sparse: few boxes overlap), short runs
+  // keep leaf boxes tight (good when curves are dense). Mean chord spacing ~ extent / sqrt(#chords).
+  uint32_t run_len = (uint32_t)o.run_length;
+  if (o.run_length <= 0) run_len = n_chords <= 4096 ? 8 : n_chords <= 65536 ? 4 : 2;
+  if (run_len > RDC_RUN) run_len = RDC_RUN;
+  k_run_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(counts, nseg, run_len, run_counts);
   BUILD_CUDA(cudaGetLastError());
   BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, run_counts, run_base, (int)(nseg + 1), stream));
   BUILD_CUDA(cudaMalloc(&scan_temp, temp_bytes ? temp_bytes : 1));
@@ -479,8 +527,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     return fail(up.status);
   }
 
-  k_emit_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(chord_geom, base, run_base, nseg, n_runs, hb, runs_in, ids_in, box_in,
-                                                           codes_in, order_in);
+  k_emit_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(chord_geom, base, run_base, nseg, n_runs, run_len, hb, runs_in, ids_in,
+                                                           box_in, codes_in, order_in);
   TEMP_CUDA(cudaGetLastError());
   size_t sort_bytes = 0;
   TEMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, codes_in, codes, order_in, order, (int)n_runs, 0, 32, stream));

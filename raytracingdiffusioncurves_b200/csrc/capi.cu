@@ -132,6 +132,7 @@ void rdc_default_accel_options(rdc_accel_options* o) {
   o->curve_width = 1e-3f;  // optixHello.cpp:95
   o->flatness_tolerance = 0.05f;
   o->max_chords_per_segment = 1024;
+  o->run_length = 0;
 }
 
 int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out) {

@@ -25,11 +25,21 @@ struct __align__(16) BvhNode {
 // Leaf primitive: up to RDC_RUN consecutive chords of one spline segment = RDC_RUN+1 points, 80 bytes =
 // five 128-bit loads. Chord j of the run joins points j and j+1; its original id is first_id + j.
 struct __align__(16) RunRecord {
-  float pts[2 * (RDC_RUN + 1)];
   uint32_t first_id;
   uint32_t count;
+  float pts[2 * (RDC_RUN + 1)];  // vector 0 = {first_id, count, P0}, vectors 1..4 = two points each
 };
 static_assert(sizeof(RunRecord) == 80, "RunRecord must be five float4");
+
+// Per spline segment: where each stop-list walk may start (rdc_walk_hint with u_min = the segment's
+// ordinal) and where it ends, plus the two per-segment lookups shading needs. 64 bytes = four 128-bit loads.
+struct __align__(16) SegWalk {
+  uint32_t left_first, left_end, right_first, right_end;
+  uint32_t blur_first, blur_end, weight_first, weight_end;
+  uint32_t degree_first, degree_end, curve, ordinal;
+  uint32_t portal_left_first, portal_left_end;  // right list's range walked on the LEFT u array (DeviceCode.cu:297)
+  uint32_t pad0, pad1;
+};
 
 struct DevStops {
   const uint2* index;  // {start,count} per curve
@@ -53,6 +63,7 @@ struct DevScene {
   const uint4* chord_ids;          // [n_chords] chord id, segment, k, K
   const uint32_t* seg_chord_base;  // [n_segments+1] id of chord 0 of each segment
   const uint32_t* seg_chord_count; // [n_segments]   K
+  const SegWalk* seg_walk;         // [n_segments]
   // acceleration structure: what rays touch
   const RunRecord* runs;           // [n_runs] Morton order
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K

@@ -140,11 +140,36 @@ RDC_HD bool rdc_is_ray_right(float t, float dx, float dy, const rdc_f2 v0, const
 // or two entries past the curve's own (start,count) range exactly like the reference does (SURVEY.md
 // Appendix A.4). Memory safety comes from the +INF sentinels the ingest appends, not from a clamp.
 // ------------------------------------------------------------------------------------------------
-RDC_HD int rdc_interp(uint32_t start, uint32_t count, float u, const float* us, float* ratio) {
-  int ind = (int)start;
-  while ((uint32_t)ind < start + count && us[ind + 1] < u) ind++;
-  *ratio = (u - us[ind]) / (us[ind + 1] - us[ind]);
+// The interpolation ratio only blends stop values (colours, blur, weights): it never decides a hit or a
+// side, so the device build may use the 2-ulp reciprocal-multiply division; host and oracle divide exactly.
+RDC_HD float rdc_ratio(float num, float den) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(num, den);
+#else
+  return num / den;
+#endif
+}
+
+// walk from `first` (any index the walk from the list's start is known to reach) up to `end` = start+count
+RDC_HD int rdc_interp_from(uint32_t first, uint32_t end, float u, const float* us, float* ratio) {
+  int ind = (int)first;
+  while ((uint32_t)ind < end && us[ind + 1] < u) ind++;
+  *ratio = rdc_ratio(u - us[ind], us[ind + 1] - us[ind]);
   return ind;
+}
+
+RDC_HD int rdc_interp(uint32_t start, uint32_t count, float u, const float* us, float* ratio) {
+  return rdc_interp_from(start, start + count, u, us, ratio);
+}
+
+// Where the walk stands once it has consumed every stop below u_min. For any u >= u_min the walk from
+// `start` passes through this index (each stop it skipped satisfies us[j+1] < u_min <= u), so starting
+// there gives the same result — also for non-monotonic lists. A spline segment's hits all have
+// u >= its ordinal, which makes this a per-segment constant (device_scene.h: SegWalk).
+RDC_HD uint32_t rdc_walk_hint(uint32_t start, uint32_t count, float u_min, const float* us) {
+  uint32_t j = start;
+  while (j < start + count && us[j + 1] < u_min) j++;
+  return j;
 }
 
 RDC_HD float rdc_lerp_stop(float a, float b, float ratio) { return (1 - ratio) * a + ratio * b; }

@@ -69,42 +69,45 @@ __device__ __forceinline__ float4 load16(const float4* p) {
   return __ldg(p);
 }
 
-// reciprocal for the slab test only (never decides a hit): one MUFU, |d| kept away from 0
+// reciprocal for the slab test only (never decides a hit): one MUFU.RCP, |d| kept away from 0
 __device__ __forceinline__ float slab_rcp(float d) {
   float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
-  return __frcp_rn(a);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 }
 
-// All chords of one run against the ray. Edge values of the shared end points are computed once.
+// All chords of one run against the ray. Edge values of the shared end points are computed once; the
+// record is read two points at a time and only as far as the run is long.
 template <bool SMEM, bool PORTALS>
 __device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
                                          uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
   const float4* rp = ac.runs + (size_t)leaf * kRunVec;
-  float p[4 * kRunVec];
-#pragma unroll
-  for (int v = 0; v < kRunVec; ++v) {
-    float4 q = load16<SMEM>(rp + v);
-    p[4 * v] = q.x; p[4 * v + 1] = q.y; p[4 * v + 2] = q.z; p[4 * v + 3] = q.w;
-  }
-  const uint32_t first_id = __float_as_uint(p[2 * (RDC_RUN + 1)]);
-  const int count = (int)__float_as_uint(p[2 * (RDC_RUN + 1) + 1]);
-  float wax = p[0] - ox, way = p[1] - oy;
+  const float4 head = load16<SMEM>(rp);
+  const uint32_t first_id = __float_as_uint(head.x);
+  const int count = (int)__float_as_uint(head.y);
+  float wax = head.z - ox, way = head.w - oy;
   float ea = rdc_edge(dx, dy, wax, way);
 #pragma unroll
-  for (int j = 0; j < RDC_RUN; ++j) {
-    // unused slots repeat the last point: their edge values are equal, never a sign change
-    float wbx = p[2 * j + 2] - ox, wby = p[2 * j + 3] - oy;
-    float eb = rdc_edge(dx, dy, wbx, wby);
-    if (j < count && (ea > 0.0f) != (eb > 0.0f)) {
-      float t, s;
-      if (rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, ea, eb, &t, &s)) {
-        const uint32_t id = first_id + (uint32_t)j;
-        if (!(PORTALS && id >= skip_lo && id <= skip_hi) && rdc_hit_closer(t, id, h.t, h.id)) {
-          h.t = t; h.s = s; h.leaf = leaf; h.j = j; h.id = id;
+  for (int v = 1; v < kRunVec; ++v) {
+    if (2 * v - 2 >= count) break;
+    const float4 q = load16<SMEM>(rp + v);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = 2 * v - 2 + half;
+      const float wbx = (half ? q.z : q.x) - ox, wby = (half ? q.w : q.y) - oy;
+      const float eb = rdc_edge(dx, dy, wbx, wby);
+      if (j < count && (ea > 0.0f) != (eb > 0.0f)) {
+        float t, s;
+        if (rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, ea, eb, &t, &s)) {
+          const uint32_t id = first_id + (uint32_t)j;
+          if (!(PORTALS && id >= skip_lo && id <= skip_hi) && rdc_hit_closer(t, id, h.t, h.id)) {
+            h.t = t; h.s = s; h.leaf = leaf; h.j = j; h.id = id;
+          }
         }
       }
+      wax = wbx; way = wby; ea = eb;
     }
-    wax = wbx; way = wby; ea = eb;
   }
 }
 
@@ -181,18 +184,17 @@ __device__ __forceinline__ void load_control_points(const DevScene& sc, uint32_t
   v[3] = {b.z, b.w};
 }
 
-__device__ __forceinline__ float scalar_stop(const DevStops& st, uint32_t curve, float cu) {
-  uint2 ix = __ldg(st.index + curve);
+__device__ __forceinline__ float scalar_stop(const DevStops& st, uint32_t first, uint32_t end, float cu) {
   float ratio;
-  int ind = rdc_interp(ix.x, ix.y, cu, st.u, &ratio);
+  int ind = rdc_interp_from(first, end, cu, st.u, &ratio);
   return rdc_lerp_stop(__ldg(st.value + ind), __ldg(st.value + ind + 1), ratio);
 }
 
-// `ix` selects the walk range, `us`/`rgb` the arrays (the portal filter mixes families, DeviceCode.cu:297)
-__device__ __forceinline__ void colour_stop(uint2 ix, const float* us, const float4* rgb, float cu, float& r, float& g,
-                                            float& b) {
+// [first,end) selects the walk range, `us`/`rgb` the arrays (the portal filter mixes families, DeviceCode.cu:297)
+__device__ __forceinline__ void colour_stop(uint32_t first, uint32_t end, const float* us, const float4* rgb, float cu,
+                                            float& r, float& g, float& b) {
   float ratio;
-  int ind = rdc_interp(ix.x, ix.y, cu, us, &ratio);
+  int ind = rdc_interp_from(first, end, cu, us, &ratio);
   float4 c0 = __ldg(rgb + ind), c1 = __ldg(rgb + ind + 1);
   r = rdc_lerp_color(c0.x, c1.x, ratio);
   g = rdc_lerp_color(c0.y, c1.y, ratio);
@@ -224,12 +226,14 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
     const uint4 id = __ldg(sc.run_ids + h.leaf);  // first chord id, segment, k of the first chord, K
     const uint32_t seg = id.y;
     const float u = rdc_hit_u((int)id.z + h.j, (int)id.w, h.s);
-    const uint32_t curve = __ldg(sc.curve_map + seg);
-    const uint32_t ordinal = __ldg(sc.curve_index + seg);
+    // walk ranges of this segment (SegWalk): the stop walks start where the segment starts
+    const uint4* wp = reinterpret_cast<const uint4*>(sc.seg_walk + seg);
+    const uint4 wc = __ldg(wp), ws = __ldg(wp + 1), wd = __ldg(wp + 2);
+    const uint32_t curve = wd.z, ordinal = wd.w;
     const float cu = u + ordinal;
-    const float blur_here = scalar_stop(sc.blur, curve, cu);
-    const float wm = scalar_stop(sc.weight, curve, cu);
-    const float e = scalar_stop(sc.weight_degree, curve, cu);
+    const float blur_here = scalar_stop(sc.blur, ws.x, ws.y, cu);
+    const float wm = scalar_stop(sc.weight, ws.z, ws.w, cu);
+    const float e = scalar_stop(sc.weight_degree, wd.x, wd.y, cu);
     const float w_here = wm * rdc_weight_falloff(h.t, e);
     rdc_f2 v[4];
     load_control_points(sc, seg, v);
@@ -254,9 +258,11 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
         float ndx = m.x * rc - m.y * rs;
         float ndy = m.y * rc + m.x * rs;
         float fr, fg, fb;
-        uint2 rix = __ldg(sc.color_right.index + curve);
-        if (right) colour_stop(rix, sc.color_right.u, sc.color_right.rgb, cu, fr, fg, fb);
-        else colour_stop(rix, sc.color_left.u, sc.color_left.rgb, cu, fr, fg, fb);  // right index on left arrays (:297)
+        if (right) colour_stop(wc.z, wc.w, sc.color_right.u, sc.color_right.rgb, cu, fr, fg, fb);
+        else {  // right list's range on the left arrays (:297)
+          const uint4 wq = __ldg(wp + 3);
+          colour_stop(wq.x, wq.y, sc.color_left.u, sc.color_left.rgb, cu, fr, fg, fb);
+        }
         Fr *= fr; Fg *= fg; Fb *= fb;
         Bp *= blur_here;
         S += 1.0f / w_here;
@@ -271,8 +277,8 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
       }
     }
     float r, g, b;
-    if (right) colour_stop(__ldg(sc.color_right.index + curve), sc.color_right.u, sc.color_right.rgb, cu, r, g, b);
-    else colour_stop(__ldg(sc.color_left.index + curve), sc.color_left.u, sc.color_left.rgb, cu, r, g, b);
+    if (right) colour_stop(wc.z, wc.w, sc.color_right.u, sc.color_right.rgb, cu, r, g, b);
+    else colour_stop(wc.x, wc.y, sc.color_left.u, sc.color_left.rgb, cu, r, g, b);
     if (PORTALS && depth > 0) {
       out.r = Fr * r; out.g = Fg * g; out.b = Fb * b;
       out.blur = Bp * blur_here;

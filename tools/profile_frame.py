@@ -19,7 +19,8 @@ def main():
     kind, payload = bench.scene_source(spec)
     host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
     stream = torch.cuda.current_stream().cuda_stream
-    scene = api.Scene(host.arrays, None, stream)
+    run_length = int(os.environ.get("RDC_RUN_LENGTH", "0"))
+    scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length), stream)
     image = torch.empty((height, width, 4), dtype=torch.float32, device="cuda")
     sigma = torch.empty((height, width), dtype=torch.float32, device="cuda")
     scratch = torch.empty_like(image)
