@@ -227,37 +227,44 @@ def main():
 
     row_begin, row_end = api.row_band(height, rank, world)
     rows = row_end - row_begin
-    max_rows = api.row_band(height, 0, world)[1]
-    band = torch.empty((max_rows, width, 4), dtype=torch.float32, device=dev)
-    sigma_band = torch.empty((max_rows, width), dtype=torch.float32, device=dev)
     flag = torch.zeros((1,), dtype=torch.float32, device=dev)
-    if rank == 0:
-        frame = torch.empty((world * max_rows, width, 4), dtype=torch.float32, device=dev) if world > 1 else band
-        sigma = torch.empty((world * max_rows, width), dtype=torch.float32, device=dev) if world > 1 else sigma_band
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
+    step_box = [0]
+
+    def params_for(step, b=row_begin, e=row_end, **kw):
+        return api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=step,
+                                        row_begin=b, row_end=e, **kw)
+
+    if world == 1:
+        band = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
+        sigma_band = torch.empty((height, width), dtype=torch.float32, device=dev)
         scratch = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
         out_frame = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
-    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def params_for(step, **kw):
-        return api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=step,
-                                        row_begin=row_begin, row_end=row_end, **kw)
+        def frame_step(step):
+            """One frame, inputs resident: render -> blur."""
+            flag.zero_()
+            p = params_for(step)
+            p.max_sigma = flag.data_ptr()
+            scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
+            api.gaussian_blur(out_frame.data_ptr(), band.data_ptr(), sigma_band.data_ptr(), scratch.data_ptr(), width, height, 0,
+                              height, flag.data_ptr(), stream)
+            return out_frame
+        launches_per_step = 3
+    else:
+        from raytracingdiffusioncurves_b200 import distributed as rd
 
-    def frame_step(step):
-        """One frame, inputs resident: render band -> (gather) -> blur on rank 0."""
-        flag.zero_()
-        p = params_for(step)
-        p.max_sigma = flag.data_ptr()
-        scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
-        if world > 1:
-            # bands are equal-sized up to one row; pad to max_rows so one gather moves them all
-            dist.gather(band, list(frame.view(world, max_rows, width, 4).unbind(0)) if rank == 0 else None, dst=0)
-            dist.gather(sigma_band, list(sigma.view(world, max_rows, width).unbind(0)) if rank == 0 else None, dst=0)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            if world > 1 and height % world != 0:
-                raise SystemExit("bench.py: image height must divide by the number of GPUs")
-            api.gaussian_blur(out_frame.data_ptr(), frame.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), width, height, 0, height,
-                              flag.data_ptr(), stream)
+        halo = rd.halo_rows(host.max_blur(depth))
+        plan = rd.BandPlan(height, width, world, rank, halo)
+        bands = rd.FrameBands(plan, dev)
+        render_band, blur_rows = api.cuda_band_callbacks(scene, lambda b, e: params_for(step_box[0], b, e), 0, stream)
+        band, sigma_band = bands.own(bands.image), bands.own(bands.sigma)
+
+        def frame_step(step):
+            """One frame over all ranks: render band -> blur-halo exchange -> local blur -> gather to rank 0."""
+            step_box[0] = step
+            return rd.render_frame(bands, render_band, blur_rows, use_blur=True)
+        launches_per_step = 1 + (2 if halo > 0 else 0)
 
     def barrier():
         if world > 1:
@@ -290,11 +297,11 @@ def main():
     rays_per_frame = float(width) * height * rpp
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: the public host-buffer call (params in, pinned image out), every step ---------------
-    e2e = None
+    # ---- e2e: host buffers in and out, every step ---------------------------------------------------
+    n_e2e = max(3, min(args.steps, 50))
+    host_img = torch.empty((height, width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
     if world == 1:
-        host_img = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
-        n_e2e = max(3, min(args.steps, 50))
+        # the public host-buffer call: frame parameters in, pinned image out
         for s in range(2):
             scene.render_frame_to_host(params_for(s), True, host_img.data_ptr(), stream)
         torch.cuda.synchronize()
@@ -302,9 +309,27 @@ def main():
         for s in range(n_e2e):
             scene.render_frame_to_host(params_for(1000 + s), True, host_img.data_ptr(), stream)
         t_e2e = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
-               "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams), "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
-               "api": "rdc_render_frame_to_host (render + blur + copy to pinned host memory + stream sync)"}
+        e2e_api = "rdc_render_frame_to_host (render + blur + copy to pinned host memory + stream sync)"
+    else:
+        def e2e_step(step):
+            frame = frame_step(step)
+            if rank == 0:
+                host_img.copy_(frame[:height], non_blocking=True)
+            torch.cuda.synchronize()
+        for s in range(2):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(n_e2e):
+            e2e_step(1000 + s)
+        barrier()
+        t_local = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_local.item())
+        e2e_api = "distributed.render_frame (band render, halo exchange, blur, gather) + copy of the frame to pinned host memory on rank 0"
+    e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
+           "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams) * world, "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
+           "api": e2e_api}
 
     # ---- roofline of the dominant kernel (k_render), measured live ---------------------------------
     roofline = None
@@ -373,11 +398,11 @@ def main():
             "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
                        "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
                        "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
+                       "runs": st.n_runs, "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
             "clocks": sampler.result(),
             "e2e": e2e,
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": launches_per_step * args.steps * world,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }

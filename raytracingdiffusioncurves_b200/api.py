@@ -187,6 +187,18 @@ class HostScene:
         except Exception:
             pass
 
+    def max_blur(self, max_trace_depth: int = 0) -> float:
+        """Upper bound of any blur_map value: sigma is a weighted mean of blur stops; each portal passed
+        multiplies it by another stop (DeviceCode.cu:311)."""
+        a = self.arrays
+        if a.n_blur == 0:
+            return 0.0
+        m = float(np.ctypeslib.as_array(a.blur, shape=(a.n_blur,)).max())
+        portals = bool((np.ctypeslib.as_array(a.curve_connect, shape=(a.n_curves,)) >= 0).any())
+        if portals and m > 1.0:
+            m = m ** (max_trace_depth + 1)
+        return max(m, 0.0)
+
     def to_numpy(self) -> dict:
         """Copies of every array (sentinels included), keyed like struct Params."""
         a = self.arrays
@@ -316,3 +328,19 @@ def row_band(height: int, rank: int, world: int) -> tuple[int, int]:
     base, rem = divmod(height, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def cuda_band_callbacks(scene: "Scene", make_params, flag_ptr: int = 0, stream: int = 0):
+    """(render_band, blur_rows) for distributed.render_frame, bound to the CUDA entry points.
+    make_params(row_begin, row_end) -> FrameParams of the frame being rendered."""
+
+    def render_band(image_rows, sigma_rows, row_begin, row_end):
+        p = make_params(row_begin, row_end)
+        p.max_sigma = flag_ptr or None
+        scene.render(p, image_rows.data_ptr(), sigma_rows.data_ptr(), stream)
+
+    def blur_rows(dest, source, sigma, scratch, height, row_begin, row_end):
+        gaussian_blur(dest.data_ptr(), source.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), source.shape[1], height,
+                      row_begin, row_end, 0, stream)
+
+    return render_band, blur_rows
