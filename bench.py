@@ -9,9 +9,10 @@ A "step" is one frame of the hot path: ray generation + closest-hit traversal + 
 xmls/arch.xml at 1920x1080, 128 rays per pixel, Orzan flag / blur / per-ray jitter as shipped, denoiser
 off. The metric is Grays/s = primary rays per second (W*H*rpp / t_frame / 1e9), whole job.
 
-N > 1: the image is cut into contiguous row bands, one per rank, scene + LBVH replicated; after rendering
-every rank sends its band to rank 0 (NCCL gather over NVLink) and rank 0 blurs the assembled frame. Total
-work is fixed as N grows ("strong" scaling); the gather is inside the timed region.
+N > 1: the image is dealt out in 16-row strips, round-robin over the ranks (scene + tree replicated); the
+strips are gathered to rank 0 over NVLink (NCCL); scenes with blur all-gather the rendered frame and every
+rank blurs one contiguous band before the gather (raytracingdiffusioncurves_b200/distributed.py). Total
+work is fixed as N grows ("strong" scaling); every exchange is inside the timed region.
 
 Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
 """
@@ -210,6 +211,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    os.environ["NCCL_DEBUG"] = os.environ.get("RDC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -255,15 +257,15 @@ def main():
         from raytracingdiffusioncurves_b200 import distributed as rd
 
         halo = rd.halo_rows(host.max_blur(depth))
-        plan = rd.BandPlan(height, width, world, rank, halo)
-        bands = rd.FrameBands(plan, dev)
-        render_band, blur_rows = api.cuda_band_callbacks(scene, lambda b, e: params_for(step_box[0], b, e), 0, stream)
-        band, sigma_band = bands.own(bands.image), bands.own(bands.sigma)
+        plan = rd.StripPlan(height, width, world, rank, halo)
+        bands = rd.FrameBuffers(plan, dev)
+        render_strips, blur_rows = api.cuda_callbacks(scene, lambda: params_for(step_box[0], 0, height), stream)
+        band, sigma_band = bands.local_image, bands.local_sigma
 
         def frame_step(step):
-            """One frame over all ranks: render band -> blur-halo exchange -> local blur -> gather to rank 0."""
+            """One frame over all ranks: render my strips -> (all-gather, local band blur) -> gather to rank 0."""
             step_box[0] = step
-            return rd.render_frame(bands, render_band, blur_rows, use_blur=True)
+            return rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
         launches_per_step = 1 + (2 if halo > 0 else 0)
 
     def barrier():
@@ -336,18 +338,25 @@ def main():
     if rank == 0:
         # work per ray from the counting build (one frame)
         stats = torch.zeros((4,), dtype=torch.int64, device=dev)
-        p = params_for(0)
+        def my_share(step):
+            q = params_for(step, 0, height)
+            if world > 1:
+                q.strip_stride, q.strip_offset = world, rank
+            return q
+
+        my_rows = sum(min(16, height - t * 16) for t in range(rank, (height + 15) // 16, world))
+        p = my_share(0)
         p.stats = stats.data_ptr()
         scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
         torch.cuda.synchronize()
         traced, nodes, chords, shaded = [float(x) for x in stats.cpu().tolist()]
-        band_rays = float(rows) * width * rpp
+        band_rays = float(my_rows) * width * rpp
         n_node, n_seg, n_hit = nodes / band_rays, chords / band_rays, shaded / band_rays
         f_ray = F_GEN + n_node * F_NODE + n_seg * F_SEG + n_hit * F_SHADE + F_ACC
         # the kernel alone, CUDA events on its stream
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(5, min(args.steps, 30))
-        pk = params_for(1)
+        pk = my_share(1)
         pk.max_sigma = flag.data_ptr()
         k0.record()
         for _ in range(reps):
@@ -373,7 +382,7 @@ def main():
                 hbm_peak = json.load(fh).get("hbm_gbs")
         except Exception:
             pass
-        alg_bytes = float(rows) * width * 20.0
+        alg_bytes = float(my_rows) * width * 20.0
         roofline = {
             "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved / fp32_peak, "traffic": None,
@@ -397,7 +406,7 @@ def main():
             "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
             "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
                        "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
-                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
+                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"16-row strips dealt round-robin over {world} GPUs, gather to rank 0" if world > 1 else "single GPU",
                        "runs": st.n_runs, "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
             "clocks": sampler.result(),

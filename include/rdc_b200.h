@@ -99,6 +99,7 @@ void rdc_scene_destroy(rdc_scene* scene);
 /* ---- per-frame render: replaces optixLaunch(pipeline, stream, d_param, sizeof(Params), &sbt, W, H, 1)
  *      (optixHello.cpp:1184) running DeviceCode.cu:85-342 ---- */
 
+#define RDC_STRIP_ROWS 16
 #define RDC_TRAVERSAL_LBVH 0
 #define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
 
@@ -110,6 +111,10 @@ typedef struct rdc_frame_params {
   uint32_t seed;                        /* Philox key word 0                                          */
   uint32_t row_begin, row_end;          /* rows [row_begin,row_end) of the full image to render; the
                                            image/blur_map pointers address row_begin (band-local)     */
+  uint32_t strip_stride, strip_offset;  /* stride > 1: the band is dealt out in strips of RDC_STRIP_ROWS
+                                           rows and this call renders strips t with t % stride == offset,
+                                           packed one after the other in the output buffers (load-balanced
+                                           multi-GPU split). stride 0 or 1: the whole band.              */
   int use_diffusion_curve_save;         /* params.h:24                                                */
   int use_aa;                           /* params.h:28                                                */
   int max_trace_depth;                  /* params.h:32, 0..31                                         */
@@ -145,6 +150,10 @@ void setupCurand(void* states, int width, int height, rdc_stream stream);
  * max_sigma (optional device float written by rdc_render) lets both passes degrade to a copy when 0. */
 int rdc_gaussian_blur(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
                       int row_begin, int row_end, const float* max_sigma, rdc_stream stream);
+/* Same, but the horizontal pass only covers the rows the band's vertical pass can reach:
+ * [row_begin - halo_rows, row_end + halo_rows) clipped to the buffer (halo_rows >= ceil(3 * largest sigma)). */
+int rdc_gaussian_blur_band(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
+                           int row_begin, int row_end, int halo_rows, const float* max_sigma, rdc_stream stream);
 
 /* ---- whole frame through host memory: the body of the reference's frame loop (optixHello.cpp:1176-1244)
  *      minus window system: render -> [blur] -> copy to host -> synchronise ---- */

@@ -121,7 +121,8 @@ Payload trace(const Ctx& c, float ox, float oy, float dx, float dy, unsigned dep
   return out;
 }
 
-void render_pixel(const Ctx& c, uint32_t ix, uint32_t iy, float* image, float* blur_map, uint32_t* hit_ids) {
+void render_pixel(const Ctx& c, uint32_t ix, uint32_t iy, uint32_t local_row, float* image, float* blur_map,
+                  uint32_t* hit_ids) {
   const rdc_frame_params& p = c.p;
   const float N = p.number_of_rays_per_pixel;
   float rot_sin, rot_cos;
@@ -133,7 +134,7 @@ void render_pixel(const Ctx& c, uint32_t ix, uint32_t iy, float* image, float* b
   float dir_x = 1, dir_y = 0;
   float color[3] = {0, 0, 0}, blur = 0, weight_total = 0;
   const uint32_t pixel = iy * p.image_width + ix;
-  const size_t local = (size_t)(iy - p.row_begin) * p.image_width + ix;
+  const size_t local = (size_t)local_row * p.image_width + ix;
   const int n_iter = (int)ceilf(N);
   for (int i = 0; i < N; i++) {
     const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, p.seed, p.frame);
@@ -189,9 +190,18 @@ int oracle_render(const rdc_scene_arrays* a, const rdc_accel_options* o, const r
   ChordSet cs = oracle::build_chords(*a, *o);
   Ctx c{*a, *p, cs};
   if (threads <= 0) threads = omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  // rows of the band, or (strip_stride > 1) the strips t % stride == offset of it, packed (rdc_b200.h)
+  const uint32_t stride = p->strip_stride > 1 ? p->strip_stride : 1, offset = p->strip_stride > 1 ? p->strip_offset : 0;
+  std::vector<uint32_t> rows;
   for (uint32_t iy = p->row_begin; iy < p->row_end; ++iy)
-    for (uint32_t ix = 0; ix < p->image_width; ++ix) render_pixel(c, ix, iy, image, blur_map, hit_ids);
+    if (((iy - p->row_begin) / RDC_STRIP_ROWS) % stride == offset) rows.push_back(iy);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (size_t r = 0; r < rows.size(); ++r) {
+    const uint32_t iy = rows[r];
+    const uint32_t rel = iy - p->row_begin;
+    const uint32_t local_row = (rel / RDC_STRIP_ROWS / stride) * RDC_STRIP_ROWS + rel % RDC_STRIP_ROWS;
+    for (uint32_t ix = 0; ix < p->image_width; ++ix) render_pixel(c, ix, iy, local_row, image, blur_map, hit_ids);
+  }
   return 0;
 }
 

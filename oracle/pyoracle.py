@@ -301,6 +301,7 @@ class FrameParams(C.Structure):
         ("image_width", C.c_uint32), ("image_height", C.c_uint32), ("number_of_rays_per_pixel", C.c_float),
         ("zoom_factor", C.c_float), ("offset_x", C.c_float), ("offset_y", C.c_float),
         ("frame", C.c_uint32), ("seed", C.c_uint32), ("row_begin", C.c_uint32), ("row_end", C.c_uint32),
+        ("strip_stride", C.c_uint32), ("strip_offset", C.c_uint32),
         ("use_diffusion_curve_save", C.c_int), ("use_aa", C.c_int), ("max_trace_depth", C.c_int),
         ("traversal", C.c_int), ("hit_ids", C.c_void_p), ("max_sigma", C.c_void_p), ("stats", C.c_void_p),
     ]

@@ -135,7 +135,7 @@ void ref_switches(int* use_diffusion_curve_save, int* use_aa, int* max_trace_dep
 int ref_render(const rdc_scene_arrays* a, const rdc_accel_options* o, const rdc_frame_params* p, float* image,
                float* blur_map, uint32_t* hit_ids, int threads) {
   if ((p->use_diffusion_curve_save != 0) != (bool)USE_DIFFUSION_CURVE_SAVE || (p->use_aa != 0) != (bool)USE_AA ||
-      p->max_trace_depth != MAX_TRACE_DEPTH)
+      p->max_trace_depth != MAX_TRACE_DEPTH || p->strip_stride > 1)
     return -1;
   oracle::ChordSet cs = oracle::build_chords(*a, *o);
   const size_t n_vertices = a->n_vertices;

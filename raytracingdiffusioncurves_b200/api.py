@@ -66,6 +66,7 @@ class FrameParams(C.Structure):
         ("image_width", C.c_uint32), ("image_height", C.c_uint32), ("number_of_rays_per_pixel", C.c_float),
         ("zoom_factor", C.c_float), ("offset_x", C.c_float), ("offset_y", C.c_float),
         ("frame", C.c_uint32), ("seed", C.c_uint32), ("row_begin", C.c_uint32), ("row_end", C.c_uint32),
+        ("strip_stride", C.c_uint32), ("strip_offset", C.c_uint32),
         ("use_diffusion_curve_save", C.c_int), ("use_aa", C.c_int), ("max_trace_depth", C.c_int),
         ("traversal", C.c_int), ("hit_ids", C.c_void_p), ("max_sigma", C.c_void_p), ("stats", C.c_void_p),
     ]
@@ -95,6 +96,8 @@ PROTOTYPES = {
     "setupCurand": (None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rdc_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p]),
+    "rdc_gaussian_blur_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p]),
     "rdc_render_frame_to_host": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_void_p, C.c_void_p]),
     "rdc_image_to_rgba8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rdc_write_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
@@ -315,6 +318,13 @@ def gaussian_blur(dest_ptr: int, src_ptr: int, sigma_ptr: int, scratch_ptr: int,
                                   C.c_void_p(max_sigma_ptr), C.c_void_p(stream)), "rdc_gaussian_blur")
 
 
+def gaussian_blur_band(dest_ptr: int, src_ptr: int, sigma_ptr: int, scratch_ptr: int, width: int, height: int,
+                       row_begin: int, row_end: int, halo_rows: int, max_sigma_ptr: int = 0, stream: int = 0) -> None:
+    _check(_lib.rdc_gaussian_blur_band(C.c_void_p(dest_ptr), C.c_void_p(src_ptr), C.c_void_p(sigma_ptr), C.c_void_p(scratch_ptr),
+                                       width, height, row_begin, row_end, halo_rows, C.c_void_p(max_sigma_ptr),
+                                       C.c_void_p(stream)), "rdc_gaussian_blur_band")
+
+
 def image_to_rgba8(image: np.ndarray, flip: bool) -> np.ndarray:
     h, w, _ = image.shape
     img = np.ascontiguousarray(image, np.float32)
@@ -330,17 +340,17 @@ def row_band(height: int, rank: int, world: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def cuda_band_callbacks(scene: "Scene", make_params, flag_ptr: int = 0, stream: int = 0):
-    """(render_band, blur_rows) for distributed.render_frame, bound to the CUDA entry points.
-    make_params(row_begin, row_end) -> FrameParams of the frame being rendered."""
+def cuda_callbacks(scene: "Scene", make_params, stream: int = 0):
+    """(render_strips, blur_rows) for distributed.render_frame, bound to the CUDA entry points.
+    make_params() -> FrameParams of the frame being rendered (whole image; the strip fields are set here)."""
 
-    def render_band(image_rows, sigma_rows, row_begin, row_end):
-        p = make_params(row_begin, row_end)
-        p.max_sigma = flag_ptr or None
-        scene.render(p, image_rows.data_ptr(), sigma_rows.data_ptr(), stream)
+    def render_strips(image, sigma, stride, offset):
+        p = make_params()
+        p.strip_stride, p.strip_offset = (stride, offset) if stride > 1 else (0, 0)
+        scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
 
-    def blur_rows(dest, source, sigma, scratch, height, row_begin, row_end):
-        gaussian_blur(dest.data_ptr(), source.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), source.shape[1], height,
-                      row_begin, row_end, 0, stream)
+    def blur_rows(dest, source, sigma, scratch, height, row_begin, row_end, halo):
+        gaussian_blur_band(dest.data_ptr(), source.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), source.shape[1], height,
+                           row_begin, row_end, halo, 0, stream)
 
-    return render_band, blur_rows
+    return render_strips, blur_rows

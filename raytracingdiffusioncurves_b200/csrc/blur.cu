@@ -43,12 +43,13 @@ __device__ __forceinline__ bool all_sigma_zero(const float* max_sigma) {
   return max_sigma != nullptr && __ldg(max_sigma) == 0.0f;
 }
 
-// rows [0,height): scratch = horizontal blur of source. With an all-zero sigma map the pass is the
+// rows [h_begin,h_end): scratch = horizontal blur of source. With an all-zero sigma map the pass is the
 // identity, so it writes `dest` directly (nothing at all when dest == source).
 __global__ void k_blur_horizontal(const float4* __restrict__ source, float4* scratch, float4* dest,
-                                  const float* __restrict__ sigma, int width, int height, const float* max_sigma) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)width * height) return;
+                                  const float* __restrict__ sigma, int width, int h_begin, int h_end, const float* max_sigma) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (size_t)width * (h_end - h_begin)) return;
+  const size_t i = j + (size_t)h_begin * width;
   if (all_sigma_zero(max_sigma)) {
     if (dest != source) dest[i] = source[i];
     return;
@@ -100,16 +101,19 @@ __global__ void k_blur_vertical(const float4* __restrict__ scratch, float4* __re
 }  // namespace
 
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
-                  int row_begin, int row_end, const float* max_sigma, cudaStream_t stream) {
+                  int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows) {
   if (!dest || !src || !sigma || !scratch || width <= 0 || height <= 0 || row_begin < 0 || row_end > height ||
       row_begin >= row_end) {
     set_error("blur: bad argument");
     return RDC_E_INVALID;
   }
-  const size_t n_all = (size_t)width * height;
+  // rows the vertical pass of the band can read
+  const int h_begin = halo_rows < 0 ? 0 : (row_begin - halo_rows > 0 ? row_begin - halo_rows : 0);
+  const int h_end = halo_rows < 0 ? height : (row_end + halo_rows < height ? row_end + halo_rows : height);
+  const size_t n_all = (size_t)width * (h_end - h_begin);
   const size_t n_band = (size_t)width * (row_end - row_begin);
   k_blur_horizontal<<<(unsigned)((n_all + kThreads - 1) / kThreads), kThreads, 0, stream>>>(src, scratch, dest, sigma, width,
-                                                                                            height, max_sigma);
+                                                                                            h_begin, h_end, max_sigma);
   RDC_CUDA(cudaGetLastError());
   k_blur_vertical<<<(unsigned)((n_band + kThreads - 1) / kThreads), kThreads, 0, stream>>>(scratch, dest, sigma, width, height,
                                                                                            row_begin, row_end, max_sigma);

@@ -178,6 +178,8 @@ void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t heig
   p->seed = 0;
   p->row_begin = 0;
   p->row_end = height;
+  p->strip_stride = 0;
+  p->strip_offset = 0;
   p->use_diffusion_curve_save = 1;  // params.h:24
   p->use_aa = 1;                    // params.h:28
   p->max_trace_depth = 2;           // params.h:32
@@ -202,6 +204,13 @@ int rdc_gaussian_blur(void* dest, const void* source, const float* sigma, void* 
   return rdc::gaussian_blur(static_cast<float4*>(dest), static_cast<const float4*>(source), sigma,
                             static_cast<float4*>(scratch), width, height, row_begin, row_end, max_sigma,
                             (cudaStream_t)stream);
+}
+
+int rdc_gaussian_blur_band(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
+                           int row_begin, int row_end, int halo_rows, const float* max_sigma, rdc_stream stream) {
+  return rdc::gaussian_blur(static_cast<float4*>(dest), static_cast<const float4*>(source), sigma,
+                            static_cast<float4*>(scratch), width, height, row_begin, row_end, max_sigma,
+                            (cudaStream_t)stream, halo_rows);
 }
 
 // Reference-named helpers. They return void like the originals; failures are readable through

@@ -100,7 +100,7 @@ int download_chords(const rdc_scene* s, float* geom, uint32_t* ids);
 int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream);
 // blur.cu
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
-                  int row_begin, int row_end, const float* max_sigma, cudaStream_t stream);
+                  int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows = -1);
 int set_float(float* dest, unsigned n, float v, cudaStream_t stream);
 }  // namespace rdc
 

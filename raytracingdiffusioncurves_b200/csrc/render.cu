@@ -37,6 +37,7 @@ struct RenderArgs {
   float* max_sigma;
   unsigned long long* stats;
   uint32_t width, height, row_begin, row_end;
+  uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kTileH: strip t belongs to t % stride == offset
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
   float n_rays;       // number_of_rays_per_pixel
   float two_over_n;   // 2 / number_of_rays_per_pixel  (DeviceCode.cu:99,120)
@@ -377,8 +378,10 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ix = tile_x * kTileW + (warp & 1) * 8 + (lane & 7);
-  const uint32_t ly = tile_y * kTileH + (warp >> 1) * 4 + (lane >> 3);  // row inside the band
-  const uint32_t iy = a.row_begin + ly;                                // row of the full image
+  const uint32_t in_tile = (warp >> 1) * 4 + (lane >> 3);
+  const uint32_t ly = tile_y * kTileH + in_tile;  // row inside the output buffer (band- or strip-local)
+  // row of the full image: contiguous band, or strip tile_y of this rank's interleaved share
+  const uint32_t iy = a.row_begin + (tile_y * a.strip_stride + a.strip_offset) * kTileH + in_tile;
   const bool valid = ix < a.width && iy < a.row_end;
 
   float sigma = 0.0f;
@@ -465,6 +468,10 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     set_error("render: rays per pixel must be in [1, 65536]");
     return RDC_E_INVALID;
   }
+  if (p.strip_stride > 1 && p.strip_offset >= p.strip_stride) {
+    set_error("render: strip_offset %u must be below strip_stride %u", p.strip_offset, p.strip_stride);
+    return RDC_E_INVALID;
+  }
   if (p.max_trace_depth < 0 || p.max_trace_depth > 31) {
     set_error("render: max_trace_depth must be in [0, 31]");
     return RDC_E_INVALID;
@@ -499,6 +506,8 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.height = p.image_height;
   a.row_begin = p.row_begin;
   a.row_end = p.row_end;
+  a.strip_stride = p.strip_stride > 1 ? p.strip_stride : 1;
+  a.strip_offset = p.strip_stride > 1 ? p.strip_offset : 0;
   a.n_iter = n_iter;
   a.n_rays = p.number_of_rays_per_pixel;
   a.two_over_n = 2 / p.number_of_rays_per_pixel;
@@ -514,7 +523,10 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.cull = p.traversal == RDC_TRAVERSAL_LBVH;  // the brute-force kernel really tests every ray against every chord
 
   const uint32_t rows = p.row_end - p.row_begin;
-  const uint32_t tiles = ((p.image_width + kTileW - 1) / kTileW) * ((rows + kTileH - 1) / kTileH);
+  const uint32_t strips = (rows + kTileH - 1) / kTileH;  // of the band; this call renders those with t % stride == offset
+  const uint32_t my_strips = a.strip_offset < strips ? (strips - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
+  if (my_strips == 0) return 0;
+  const uint32_t tiles = ((p.image_width + kTileW - 1) / kTileW) * my_strips;
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;

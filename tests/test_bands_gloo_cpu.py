@@ -27,17 +27,35 @@ def free_port():
 def oracle_callbacks(scene, width, height, rpp, zoom):
     oracle = po.Oracle("port")
 
-    def render_band(image_rows, sigma_rows, row_begin, row_end):
-        p = po.make_params(width, height, rpp, zoom_factor=zoom, row_begin=row_begin, row_end=row_end)
-        img, sig, _ = oracle.render(scene, p, threads=2)
-        image_rows.copy_(torch.from_numpy(img))
-        sigma_rows.copy_(torch.from_numpy(sig))
+    def render_strips(image, sigma, stride, offset):
+        p = po.make_params(width, height, rpp, zoom_factor=zoom, strip_stride=stride if stride > 1 else 0,
+                           strip_offset=offset if stride > 1 else 0)
+        rows = image.shape[0]
+        p_rows = po.make_params(width, height, rpp)  # only to size the oracle's output arrays
+        del p_rows
+        img, sig = render_packed(oracle, scene, p, rows)
+        image.copy_(torch.from_numpy(img))
+        sigma.copy_(torch.from_numpy(sig))
 
-    def blur_rows(dest, source, sigma, scratch, rows, row_begin, row_end):
+    def blur_rows(dest, source, sigma, scratch, rows, row_begin, row_end, halo):
         out = oracle.blur(source[:rows].numpy(), sigma[:rows].numpy(), threads=2)
         dest[row_begin:row_end].copy_(torch.from_numpy(out[row_begin:row_end]))
 
-    return render_band, blur_rows
+    return render_strips, blur_rows
+
+
+def render_packed(oracle, scene, p, rows):
+    """oracle_render into buffers of `rows` packed rows (the strips of one rank)."""
+    import ctypes as C
+
+    a, keep = po.arrays_from_dict(scene)
+    img = np.zeros((rows, p.image_width, 4), np.float32)
+    sig = np.zeros((rows, p.image_width), np.float32)
+    accel = po.make_accel()
+    rc = oracle._render(C.byref(a), C.byref(accel), C.byref(p), img.ctypes.data, sig.ctypes.data, None, 2)
+    assert rc == 0
+    del keep
+    return img, sig
 
 
 def worker(rank, world, port, scene_file, width, height, rpp, halo, out_path):
@@ -47,10 +65,10 @@ def worker(rank, world, port, scene_file, width, height, rpp, halo, out_path):
     try:
         scene = po.ingest_xml(os.path.join(XML, scene_file), True)
         zoom = scene["image_height"] / height
-        plan = rd.BandPlan(height, width, world, rank, halo)
-        bands = rd.FrameBands(plan, torch.device("cpu"))
-        render_band, blur_rows = oracle_callbacks(scene, width, height, rpp, zoom)
-        frame = rd.render_frame(bands, render_band, blur_rows, use_blur=True)
+        plan = rd.StripPlan(height, width, world, rank, halo)
+        buf = rd.FrameBuffers(plan, torch.device("cpu"))
+        render_strips, blur_rows = oracle_callbacks(scene, width, height, rpp, zoom)
+        frame = rd.render_frame(buf, render_strips, blur_rows, use_blur=True)
         if rank == 0:
             np.save(out_path, frame.numpy())
             assert frame.shape == (height, width, 4)
@@ -70,16 +88,17 @@ def single_process_frame(scene_file, width, height, rpp):
 
 
 @pytest.mark.parametrize("world,scene_file,height,case", [
-    (2, "DiffusionCurvePack/lady_bug.xml", 60, "halo exchange"),      # max blur stop 7 -> halo 21 <= 30 rows
-    (3, "DiffusionCurvePack/lady_bug.xml", 66, "halo exchange, 3 ranks"),
-    (2, "DiffusionCurvePack/face.xml", 40, "halo deeper than a band"),   # max blur stop 16 -> halo 48 > 20 rows
-    (2, "arch.xml", 31, "no blur, uneven bands"),
+    (2, "DiffusionCurvePack/lady_bug.xml", 60, "blur: all-gather, local band blur, gather"),
+    (3, "DiffusionCurvePack/lady_bug.xml", 70, "blur, 3 ranks, ragged last strip"),
+    (2, "DiffusionCurvePack/face.xml", 40, "blur reach deeper than a band"),
+    (2, "arch.xml", 37, "no blur: gather of packed strips, uneven strip counts"),
+    (3, "arch.xml", 16, "fewer strips than ranks"),
 ])
-def test_bands_reassemble_bit_exactly(world, scene_file, height, case, tmp_path):
+def test_strips_reassemble_bit_exactly(world, scene_file, height, case, tmp_path):
     po.build()
     width, rpp = 36, 6
     want, sigma_seen, sigma_bound = single_process_frame(scene_file, width, height, rpp)
-    assert sigma_seen <= sigma_bound + 1e-6  # the static halo bound really bounds the blur map
+    assert sigma_seen <= sigma_bound + 1e-6  # the static bound really bounds the blur map
     halo = rd.halo_rows(sigma_bound)
     out = str(tmp_path / "frame.npy")
     mp.spawn(worker, args=(world, free_port(), scene_file, width, height, rpp, halo, out), nprocs=world, join=True)
@@ -87,14 +106,26 @@ def test_bands_reassemble_bit_exactly(world, scene_file, height, case, tmp_path)
     assert np.array_equal(got[..., :3].view(np.uint32), want[..., :3].view(np.uint32)), case
 
 
-def test_band_plan_arithmetic():
+def test_strip_plan_arithmetic():
     assert [rd.row_band(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert rd.halo_rows(0.0) == 0 and rd.halo_rows(1.5) == 5 and rd.halo_rows(16) == 48
-    p = rd.BandPlan(1080, 1920, 8, 3, 48)
-    assert (p.begin, p.end, p.top, p.bottom, p.exchange, p.buffer_rows) == (405, 540, 48, 48, True, 231)
-    edge = rd.BandPlan(1080, 1920, 8, 0, 48)
-    assert (edge.top, edge.bottom) == (0, 48)
-    deep = rd.BandPlan(64, 32, 8, 2, 48)
-    assert not deep.exchange and deep.top == 0 and deep.bottom == 0
-    single = rd.BandPlan(64, 32, 1, 0, 48)
-    assert not single.exchange and single.buffer_rows == 64
+    p = rd.StripPlan(1080, 1920, 8, 3, 0)
+    assert p.n_strips == 68 and p.packed_rows == 9 * 16 and p.local_strips == 9
+    assert rd.StripPlan(1080, 1920, 8, 4, 0).local_strips == 8
+    idx = p.source_index()
+    assert idx[0] == 0 and idx[16] == p.packed_rows and idx[8 * 16] == 16 and idx[1079] == 3 * p.packed_rows + 8 * 16 + 7
+    assert len(set(idx.tolist())) == 1080
+    q = rd.StripPlan(100, 8, 3, 1, 5)
+    bi = q.band_index()
+    assert bi[0] == 0 and bi[34] == q.max_band_rows and bi[99] == 2 * q.max_band_rows + 32
+    assert rd.StripPlan(16, 8, 3, 2, 0).local_strips == 0
+
+
+def test_oracle_strips_equal_rows_of_the_full_frame():
+    oracle = po.Oracle("port")
+    scene = po.ingest_xml(os.path.join(XML, "arch.xml"), True)
+    full, _, _ = oracle.render(scene, po.make_params(20, 50, 8, zoom_factor=10.0))
+    p = po.make_params(20, 50, 8, zoom_factor=10.0, strip_stride=2, strip_offset=1)
+    img, _ = render_packed(oracle, scene, p, 32)
+    assert np.array_equal(img[:16].view(np.uint32), full[16:32].view(np.uint32))
+    assert np.array_equal(img[16:18].view(np.uint32), full[48:50].view(np.uint32))

@@ -124,6 +124,33 @@ def test_row_bands_concatenate_bit_exactly(xml_dir, api):
             assert np.array_equal(bits(np.concatenate([q[key] for q in parts])), bits(full[key])), (world, key)
 
 
+def test_interleaved_strips_reassemble_bit_exactly(xml_dir, api):
+    """The multi-GPU split (16-row strips dealt round-robin) emulated on one GPU: every rank's packed
+    strips, put back in order with distributed.StripPlan.source_index, equal the one-call frame."""
+    import torch
+
+    from raytracingdiffusioncurves_b200 import distributed as rd
+
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))
+    w, h, n = 72, 83, 8
+    full = r.render(api.default_frame_params(w, h, n, zoom_factor=512 / h), want_hits=True)
+    for world in (2, 3, 8):
+        plan = rd.StripPlan(h, w, world, 0, 0)
+        images, sigmas = [], []
+        for rank in range(world):
+            image = torch.zeros((plan.packed_rows, w, 4), dtype=torch.float32, device="cuda")
+            sigma = torch.zeros((plan.packed_rows, w), dtype=torch.float32, device="cuda")
+            p = api.default_frame_params(w, h, n, zoom_factor=512 / h, strip_stride=world, strip_offset=rank)
+            r.scene.render(p, image.data_ptr(), sigma.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            images.append(image)
+            sigmas.append(sigma)
+        idx = plan.source_index().cuda()
+        got = torch.cat(images).index_select(0, idx).cpu().numpy()
+        got_sigma = torch.cat(sigmas).index_select(0, idx).cpu().numpy()
+        assert np.array_equal(bits(got), bits(full["image"])), world
+        assert np.array_equal(bits(got_sigma), bits(full["blur_map"])), world
+
+
 def test_lbvh_equals_brute_force_at_headline_size(xml_dir, api):
     """Size-independent property at BASELINE's config 2 (arch.xml 1920x1080, 128 rays/pixel):
     the LBVH traversal and the no-tree kernel agree on every one of the 265 M first hits."""

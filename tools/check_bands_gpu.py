@@ -30,14 +30,14 @@ def main():
         scene = api.Scene(host.arrays, None, stream)
         zoom = host.arrays.image_height / h
 
-        def make(b, e):
+        def make(b=0, e=h):
             return api.default_frame_params(w, h, rpp, zoom_factor=zoom, row_begin=b, row_end=e, frame=3)
 
         halo = rd.halo_rows(host.max_blur(2))
-        plan = rd.BandPlan(h, w, world, rank, halo)
-        bands = rd.FrameBands(plan, dev)
-        render_band, blur_rows = api.cuda_band_callbacks(scene, make, 0, stream)
-        frame = rd.render_frame(bands, render_band, blur_rows, use_blur=True)
+        plan = rd.StripPlan(h, w, world, rank, halo)
+        bands = rd.FrameBuffers(plan, dev)
+        render_strips, blur_rows = api.cuda_callbacks(scene, make, stream)
+        frame = rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
         torch.cuda.synchronize()
         if rank == 0:
             image = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
@@ -51,7 +51,7 @@ def main():
                 want = image
             torch.cuda.synchronize()
             same = torch.equal(frame[:h, :, :3].contiguous().view(torch.int32), want[..., :3].contiguous().view(torch.int32))
-            print(f"{'OK  ' if same else 'FAIL'} {name} {w}x{h}@{rpp} world={world} halo={halo} exchange={plan.exchange}", flush=True)
+            print(f"{'OK  ' if same else 'FAIL'} {name} {w}x{h}@{rpp} world={world} halo={halo}", flush=True)
             failures += 0 if same else 1
         dist.barrier()
     dist.destroy_process_group()
