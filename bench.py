@@ -211,7 +211,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
-    os.environ["NCCL_DEBUG"] = os.environ.get("RDC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    if "RDC_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["RDC_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout; keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

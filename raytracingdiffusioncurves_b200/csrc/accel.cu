@@ -417,6 +417,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   uint32_t* base = up.alloc<uint32_t>(nseg + 1);
   Bounds* bounds = up.alloc<Bounds>(1);
   s->zero_sigma = up.alloc<float>(1);
+  s->work_counters = up.alloc<unsigned int>(2);
   auto fail = [&](int code) {
     destroy_scene(s);
     return code;
@@ -429,6 +430,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   } while (0)
   BUILD_CUDA(cudaMemsetAsync(counts, 0, (nseg + 1) * sizeof(uint32_t), stream));
   BUILD_CUDA(cudaMemsetAsync(s->zero_sigma, 0, sizeof(float), stream));
+  BUILD_CUDA(cudaMemsetAsync(s->work_counters, 0, 2 * sizeof(unsigned int), stream));
   k_chord_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(d.vertices, d.segment_indices, nseg, o.flatness_tolerance,
                                                             o.max_chords_per_segment, counts);
   BUILD_CUDA(cudaGetLastError());

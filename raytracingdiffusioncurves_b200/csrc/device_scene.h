@@ -82,6 +82,8 @@ struct rdc_scene {
   float base_dirs_n = -1.0f;
   uint32_t base_dirs_capacity = 0;
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
+  unsigned int* work_counters = nullptr;  // k_render's tile counter pair (one render in flight per handle)
+  uint32_t grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // SM-filling grid size per kernel variant
   // frame buffers of rdc_render_frame_to_host, grown on demand and kept (no per-frame allocation)
   float4* frame_image = nullptr;
   float4* frame_scratch = nullptr;

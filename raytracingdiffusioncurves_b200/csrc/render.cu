@@ -22,7 +22,10 @@
 namespace rdc {
 namespace {
 
-constexpr int kTileW = 16, kTileH = 16, kBlock = kTileW * kTileH;
+constexpr int kBlock = 256;
+constexpr int kWarpTileW = 8, kWarpTileH = 4;   // pixels one warp renders per fetch
+constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
+static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
 constexpr size_t kSmemSceneLimit = 40 * 1024;  // stage nodes + runs in shared memory below this
@@ -37,7 +40,9 @@ struct RenderArgs {
   float* max_sigma;
   unsigned long long* stats;
   uint32_t width, height, row_begin, row_end;
-  uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kTileH: strip t belongs to t % stride == offset
+  uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kStripRows: strip t belongs to t % stride == offset
+  uint32_t local_rows;                  // rows of the output buffers this launch covers
+  unsigned int* work;                   // [0] next warp tile, [1] warps finished (self-rewinding)
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
   float n_rays;       // number_of_rays_per_pixel
   float two_over_n;   // 2 / number_of_rays_per_pixel  (DeviceCode.cu:99,120)
@@ -373,30 +378,34 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
   }
 
-  // 16x16 pixel tile per block, 8x4 pixels per warp
-  const uint32_t tiles_x = (a.width + kTileW - 1) / kTileW;
-  const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ix = tile_x * kTileW + (warp & 1) * 8 + (lane & 7);
-  const uint32_t in_tile = (warp >> 1) * 4 + (lane >> 3);
-  const uint32_t ly = tile_y * kTileH + in_tile;  // row inside the output buffer (band- or strip-local)
-  // row of the full image: contiguous band, or strip tile_y of this rank's interleaved share
-  const uint32_t iy = a.row_begin + (tile_y * a.strip_stride + a.strip_offset) * kTileH + in_tile;
-  const bool valid = ix < a.width && iy < a.row_end;
-
-  float sigma = 0.0f;
+  // Persistent warps: every warp of the (SM-filling) grid keeps fetching 8x4-pixel tiles from one global
+  // counter until the image is done. Tiles differ in cost by an order of magnitude (how many rays reach
+  // the scene, how deep they go); fetching at warp granularity keeps every scheduler busy to the end.
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
+  const uint32_t n_tiles = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
+  float sigma_max = 0.0f;
   Counters cnt;
-  if (valid) {
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.work, 1u);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= n_tiles) break;
+    const uint32_t ix = (tile % tiles_x) * kWarpTileW + (lane & 7);
+    const uint32_t ly = (tile / tiles_x) * kWarpTileH + (lane >> 3);  // row inside the output buffer (band- or strip-local)
+    // row of the full image: contiguous band, or strip (ly / 16) of this rank's interleaved share
+    const uint32_t iy = a.row_begin + ((ly / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly % kStripRows;
+    if (ix >= a.width || iy >= a.row_end) continue;
+
     // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
     const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
     const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
                                  : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
-    const uint32_t pixel = iy * a.width + ix;  // global pixel index: band-independent random numbers
+    const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
     const size_t local_pixel = (size_t)ly * a.width + ix;
     int cull_first = 0, cull_span = 0;
     const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
-    // N >= 8 keeps the jitter angle within the polynomial's range: no range reduction (bit-identical)
-    const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
     for (int i = 0; i < a.n_iter; ++i) {
       if (culling) {
@@ -432,13 +441,13 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     }
     // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
     a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
-    sigma = blur / weight_total;
+    const float sigma = blur / weight_total;
     a.blur_map[local_pixel] = sigma;
+    sigma_max = fmaxf(sigma_max, sigma);  // NaN and negative sigmas do not raise the flag (the blur yields NaN for them either way)
   }
+  __syncwarp();
   if (a.max_sigma) {
-    // NaN and negative sigmas do not raise the flag: such pixels produce NaN in the blur either way
-    unsigned int bits = __float_as_uint(fmaxf(sigma, 0.0f));
-    bits = __reduce_max_sync(0xFFFFFFFFu, bits);
+    unsigned int bits = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(sigma_max));
     if (lane == 0 && bits != 0u) atomicMax(reinterpret_cast<unsigned int*>(a.max_sigma), bits);
   }
   if (STATS) {
@@ -449,6 +458,14 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       atomicAdd(a.stats + 1, (unsigned long long)n);
       atomicAdd(a.stats + 2, (unsigned long long)c);
       atomicAdd(a.stats + 3, (unsigned long long)h);
+    }
+  }
+  // the last warp to leave rewinds the tile counter for the next launch on this handle
+  if (lane == 0) {
+    const unsigned int warps = gridDim.x * (kBlock / 32);
+    if (atomicAdd(a.work + 1, 1u) == warps - 1) {
+      a.work[0] = 0u;
+      a.work[1] = 0u;
     }
   }
 }
@@ -523,21 +540,41 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.cull = p.traversal == RDC_TRAVERSAL_LBVH;  // the brute-force kernel really tests every ray against every chord
 
   const uint32_t rows = p.row_end - p.row_begin;
-  const uint32_t strips = (rows + kTileH - 1) / kTileH;  // of the band; this call renders those with t % stride == offset
+  const uint32_t strips = (rows + kStripRows - 1) / kStripRows;  // of the band; this call renders those with t % stride == offset
   const uint32_t my_strips = a.strip_offset < strips ? (strips - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
   if (my_strips == 0) return 0;
-  const uint32_t tiles = ((p.image_width + kTileW - 1) / kTileW) * my_strips;
+  a.local_rows = a.strip_stride > 1 ? my_strips * kStripRows : rows;
+  a.work = s->work_counters;
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;
   const size_t dyn = smem ? scene_bytes : 0;
-  if (p.stats) {  // counting build
-    if (smem) k_render<true, true, true><<<tiles, kBlock, dyn, stream>>>(a);
-    else k_render<false, true, true><<<tiles, kBlock, 0, stream>>>(a);
-  } else if (smem && portals) k_render<true, true, false><<<tiles, kBlock, dyn, stream>>>(a);
-  else if (smem) k_render<true, false, false><<<tiles, kBlock, dyn, stream>>>(a);
-  else if (portals) k_render<false, true, false><<<tiles, kBlock, 0, stream>>>(a);
-  else k_render<false, false, false><<<tiles, kBlock, 0, stream>>>(a);
+  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build
+  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0);
+  void (*kernel)(RenderArgs) = nullptr;
+  switch (variant) {
+    case 0: kernel = k_render<false, false, false>; break;
+    case 1: kernel = k_render<true, false, false>; break;
+    case 2: kernel = k_render<false, true, false>; break;
+    case 3: kernel = k_render<true, true, false>; break;
+    case 6: kernel = k_render<false, true, true>; break;
+    default: kernel = k_render<true, true, true>; break;
+  }
+  if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
+    int per_sm = 0, sms = 0;
+    RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
+    RDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (per_sm < 1 || sms < 1) {
+      set_error("render: the kernel does not fit an SM");
+      return RDC_E_LIMIT;
+    }
+    s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
+  }
+  const uint32_t warp_tiles = ((p.image_width + kWarpTileW - 1) / kWarpTileW) * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  uint32_t grid = s->grid_blocks[variant];
+  const uint32_t needed = (warp_tiles + kBlock / 32 - 1) / (kBlock / 32);
+  if (grid > needed) grid = needed;
+  kernel<<<grid, kBlock, dyn, stream>>>(a);
   RDC_CUDA(cudaGetLastError());
   return 0;
 }
