@@ -23,7 +23,8 @@ namespace rdc {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kWarpTileW = 8, kWarpTileH = 4;   // pixels one warp renders per fetch
+constexpr int kWarpTileW = 8, kWarpTileH = 1;   // pixels one warp renders per fetch
+constexpr int kPhases = 32 / (kWarpTileW * kWarpTileH);  // lanes per pixel: lane q of a pixel traces rays i = q (mod kPhases)
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
@@ -378,10 +379,13 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
   }
 
-  // Persistent warps: every warp of the (SM-filling) grid keeps fetching 8x4-pixel tiles from one global
-  // counter until the image is done. Tiles differ in cost by an order of magnitude (how many rays reach
-  // the scene, how deep they go); fetching at warp granularity keeps every scheduler busy to the end.
+  // Persistent warps: every warp of the (SM-filling) grid keeps fetching tiles of 8 pixels from one global
+  // counter until the image is done. Each pixel is shared by kPhases lanes, lane q tracing rays q, q+kPhases,
+  // ...: a unit of work is then 8 pixels x N rays with a serial chain of only N/kPhases rays per lane.
+  // Tiles differ in cost by an order of magnitude (how many rays reach the scene, how deep they go); small
+  // units fetched at warp granularity keep every scheduler busy to the end of the frame.
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t px = lane % (kWarpTileW * kWarpTileH), phase = lane / (kWarpTileW * kWarpTileH);
   const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
   const uint32_t n_tiles = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
   const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
@@ -392,58 +396,70 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     if (lane == 0) tile = atomicAdd(a.work, 1u);
     tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
     if (tile >= n_tiles) break;
-    const uint32_t ix = (tile % tiles_x) * kWarpTileW + (lane & 7);
-    const uint32_t ly = (tile / tiles_x) * kWarpTileH + (lane >> 3);  // row inside the output buffer (band- or strip-local)
+    const uint32_t ix = (tile % tiles_x) * kWarpTileW + px % kWarpTileW;
+    const uint32_t ly = (tile / tiles_x) * kWarpTileH + px / kWarpTileW;  // row inside the output buffer (band- or strip-local)
     // row of the full image: contiguous band, or strip (ly / 16) of this rank's interleaved share
     const uint32_t iy = a.row_begin + ((ly / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly % kStripRows;
-    if (ix >= a.width || iy >= a.row_end) continue;
-
-    // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
-    const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
-    const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
-                                 : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
-    const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
+    const bool valid = ix < a.width && iy < a.row_end;
     const size_t local_pixel = (size_t)ly * a.width + ix;
-    int cull_first = 0, cull_span = 0;
-    const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
-    for (int i = 0; i < a.n_iter; ++i) {
-      if (culling) {
-        int rel = i - cull_first;
-        if (rel < 0) rel += a.n_iter;
-        if (rel > cull_span) {  // cannot reach the scene: a miss, adds nothing
-          if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
-          continue;
+    if (valid) {
+      // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
+      const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
+      const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
+                                   : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
+      const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
+      int cull_first = 0, cull_span = 0;
+      const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
+      for (int i = (int)phase; i < a.n_iter; i += kPhases) {
+        if (culling) {
+          int rel = i - cull_first;
+          if (rel < 0) rel += a.n_iter;
+          if (rel > cull_span) {  // cannot reach the scene: a miss, adds nothing
+            if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
+            continue;
+          }
         }
+        const float2 base = __ldg(a.base_dirs + i);
+        // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
+        const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
+        float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
+        if (a.use_aa) {
+          float js, jc;
+          const float ang = a.two_over_n * rdc_u01(rnd.x);
+          if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
+          else rdc_sincospi(ang, &js, &jc);
+          dx = base.x * jc - base.y * js;
+          dy = base.x * js + base.y * jc;
+          ox = base_x + rdc_u01(rnd.y) * a.zoom;
+          oy = base_y + rdc_u01(rnd.z) * a.zoom;
+        }
+        uint32_t first_hit;
+        Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
+        if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
+        weight_total += s.w;
+        cr += s.r * s.w;
+        cg += s.g * s.w;
+        cb += s.b * s.w;
+        blur += s.blur * s.w;
       }
-      const float2 base = __ldg(a.base_dirs + i);
-      // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
-      const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
-      float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
-      if (a.use_aa) {
-        float js, jc;
-        const float ang = a.two_over_n * rdc_u01(rnd.x);
-        if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
-        else rdc_sincospi(ang, &js, &jc);
-        dx = base.x * jc - base.y * js;
-        dy = base.x * js + base.y * jc;
-        ox = base_x + rdc_u01(rnd.y) * a.zoom;
-        oy = base_y + rdc_u01(rnd.z) * a.zoom;
-      }
-      uint32_t first_hit;
-      Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
-      if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
-      weight_total += s.w;
-      cr += s.r * s.w;
-      cg += s.g * s.w;
-      cb += s.b * s.w;
-      blur += s.blur * s.w;
     }
-    // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
-    a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
-    const float sigma = blur / weight_total;
-    a.blur_map[local_pixel] = sigma;
-    sigma_max = fmaxf(sigma_max, sigma);  // NaN and negative sigmas do not raise the flag (the blur yields NaN for them either way)
+    // the pixel's kPhases partial sums, combined in a fixed (butterfly) order: the same on every GPU split
+#pragma unroll
+    for (int m = kWarpTileW * kWarpTileH; m < 32; m <<= 1) {
+      weight_total += __shfl_xor_sync(0xFFFFFFFFu, weight_total, m);
+      cr += __shfl_xor_sync(0xFFFFFFFFu, cr, m);
+      cg += __shfl_xor_sync(0xFFFFFFFFu, cg, m);
+      cb += __shfl_xor_sync(0xFFFFFFFFu, cb, m);
+      blur += __shfl_xor_sync(0xFFFFFFFFu, blur, m);
+    }
+    if (valid && phase == 0) {
+      // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
+      a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
+      const float sigma = blur / weight_total;
+      a.blur_map[local_pixel] = sigma;
+      sigma_max = fmaxf(sigma_max, sigma);  // NaN and negative sigmas do not raise the flag (the blur yields NaN for them either way)
+    }
   }
   __syncwarp();
   if (a.max_sigma) {
