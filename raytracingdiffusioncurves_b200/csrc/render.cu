@@ -23,8 +23,9 @@ namespace rdc {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kWarpTileW = 8, kWarpTileH = 1;   // pixels one warp renders per fetch
-constexpr int kPhases = 32 / (kWarpTileW * kWarpTileH);  // lanes per pixel: lane q of a pixel traces rays i = q (mod kPhases)
+constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a big work unit: 8x4 pixels, one lane per pixel
+constexpr int kPhases = 4;                      // a small work unit: 8x1 pixels, kPhases lanes per pixel, lane q
+                                                // of a pixel tracing rays i = q (mod kPhases)
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
@@ -43,6 +44,7 @@ struct RenderArgs {
   uint32_t width, height, row_begin, row_end;
   uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kStripRows: strip t belongs to t % stride == offset
   uint32_t local_rows;                  // rows of the output buffers this launch covers
+  uint32_t big_rows;                    // rows [0,big_rows) go out as big units, the rest as small ones
   unsigned int* work;                   // [0] next warp tile, [1] warps finished (self-rewinding)
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
   float n_rays;       // number_of_rays_per_pixel
@@ -379,15 +381,17 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
   }
 
-  // Persistent warps: every warp of the (SM-filling) grid keeps fetching tiles of 8 pixels from one global
-  // counter until the image is done. Each pixel is shared by kPhases lanes, lane q tracing rays q, q+kPhases,
-  // ...: a unit of work is then 8 pixels x N rays with a serial chain of only N/kPhases rays per lane.
-  // Tiles differ in cost by an order of magnitude (how many rays reach the scene, how deep they go); small
-  // units fetched at warp granularity keep every scheduler busy to the end of the frame.
+  // Persistent warps: every warp of the (SM-filling) grid keeps fetching work units from one global
+  // counter until the image is done. Units differ in cost by an order of magnitude (how many rays reach
+  // the scene, how deep they go). The bulk of the image goes out as 8x4-pixel units, one lane per pixel,
+  // all lanes on the same ray index — the most coherent mapping. A lane then runs N rays back to back,
+  // and a warp left alone with such a unit at the end of the frame would take ~0.4 ms at 1080p; so the
+  // last rows go out as 8x1-pixel units with kPhases lanes per pixel (N/kPhases rays per lane), whose
+  // partial sums are combined by shuffles in a fixed order.
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t px = lane % (kWarpTileW * kWarpTileH), phase = lane / (kWarpTileW * kWarpTileH);
   const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
-  const uint32_t n_tiles = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  const uint32_t n_big = tiles_x * ((a.big_rows + kWarpTileH - 1) / kWarpTileH);
+  const uint32_t n_tiles = n_big + tiles_x * (a.local_rows - a.big_rows);
   const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
   float sigma_max = 0.0f;
   Counters cnt;
@@ -396,11 +400,16 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     if (lane == 0) tile = atomicAdd(a.work, 1u);
     tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
     if (tile >= n_tiles) break;
-    const uint32_t ix = (tile % tiles_x) * kWarpTileW + px % kWarpTileW;
-    const uint32_t ly = (tile / tiles_x) * kWarpTileH + px / kWarpTileW;  // row inside the output buffer (band- or strip-local)
+    const bool big = tile < n_big;
+    const uint32_t unit = big ? tile : tile - n_big;
+    const int phases = big ? 1 : kPhases;
+    const uint32_t phase = big ? 0u : lane / kWarpTileW;
+    const uint32_t ix = (unit % tiles_x) * kWarpTileW + lane % kWarpTileW;
+    // row inside the output buffer (band- or strip-local)
+    const uint32_t ly = big ? (unit / tiles_x) * kWarpTileH + lane / kWarpTileW : a.big_rows + unit / tiles_x;
     // row of the full image: contiguous band, or strip (ly / 16) of this rank's interleaved share
     const uint32_t iy = a.row_begin + ((ly / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly % kStripRows;
-    const bool valid = ix < a.width && iy < a.row_end;
+    const bool valid = ix < a.width && iy < a.row_end && (!big || ly < a.big_rows);
     const size_t local_pixel = (size_t)ly * a.width + ix;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
     if (valid) {
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
       int cull_first = 0, cull_span = 0;
       const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
-      for (int i = (int)phase; i < a.n_iter; i += kPhases) {
+      for (int i = (int)phase; i < a.n_iter; i += phases) {
         if (culling) {
           int rel = i - cull_first;
           if (rel < 0) rel += a.n_iter;
@@ -444,14 +453,15 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         blur += s.blur * s.w;
       }
     }
-    // the pixel's kPhases partial sums, combined in a fixed (butterfly) order: the same on every GPU split
+    if (!big) {  // the pixel's kPhases partial sums, combined in a fixed (butterfly) order
 #pragma unroll
-    for (int m = kWarpTileW * kWarpTileH; m < 32; m <<= 1) {
-      weight_total += __shfl_xor_sync(0xFFFFFFFFu, weight_total, m);
-      cr += __shfl_xor_sync(0xFFFFFFFFu, cr, m);
-      cg += __shfl_xor_sync(0xFFFFFFFFu, cg, m);
-      cb += __shfl_xor_sync(0xFFFFFFFFu, cb, m);
-      blur += __shfl_xor_sync(0xFFFFFFFFu, blur, m);
+      for (int m = kWarpTileW; m < 32; m <<= 1) {
+        weight_total += __shfl_xor_sync(0xFFFFFFFFu, weight_total, m);
+        cr += __shfl_xor_sync(0xFFFFFFFFu, cr, m);
+        cg += __shfl_xor_sync(0xFFFFFFFFu, cg, m);
+        cb += __shfl_xor_sync(0xFFFFFFFFu, cb, m);
+        blur += __shfl_xor_sync(0xFFFFFFFFu, blur, m);
+      }
     }
     if (valid && phase == 0) {
       // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
@@ -586,7 +596,30 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     }
     s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
   }
-  const uint32_t warp_tiles = ((p.image_width + kWarpTileW - 1) / kWarpTileW) * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  // Rows that go out as small units: about 1.5 big units' worth of pixels per resident warp, at most half
+  // the image. Which rows are "last" is fixed by the image size and the split alone, so a pixel's value does
+  // not depend on the GPU it runs on... but it does depend on the unit kind (summation order), hence the
+  // boundary is derived from the FULL image height: a row is small in every split or in none.
+  const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
+  const uint64_t resident_warps = (uint64_t)s->grid_blocks[variant] * (kBlock / 32);
+  uint64_t small_pixels = resident_warps * 48;
+  const uint64_t frame_pixels = (uint64_t)p.image_width * p.image_height;
+  if (small_pixels > frame_pixels / 2) small_pixels = frame_pixels / 2;
+  uint32_t small_rows_global = (uint32_t)((small_pixels + p.image_width - 1) / p.image_width);
+  small_rows_global = (small_rows_global + kStripRows - 1) / kStripRows * kStripRows;  // whole strips
+  const uint32_t big_limit_global = p.image_height > small_rows_global ? (p.image_height - small_rows_global) / kStripRows * kStripRows : 0;
+  // local rows whose global row is below big_limit_global
+  uint32_t big_rows = 0;
+  if (a.strip_stride > 1) {
+    const uint32_t big_strips_global = big_limit_global / kStripRows;  // strips [0, big_strips_global) are big
+    const uint32_t mine = a.strip_offset < big_strips_global ? (big_strips_global - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
+    big_rows = mine * kStripRows;
+  } else {
+    big_rows = big_limit_global > p.row_begin ? big_limit_global - p.row_begin : 0;
+  }
+  if (big_rows > a.local_rows) big_rows = a.local_rows;
+  a.big_rows = big_rows;
+  const uint32_t warp_tiles = tiles_x * ((big_rows + kWarpTileH - 1) / kWarpTileH) + tiles_x * (a.local_rows - big_rows);
   uint32_t grid = s->grid_blocks[variant];
   const uint32_t needed = (warp_tiles + kBlock / 32 - 1) / (kBlock / 32);
   if (grid > needed) grid = needed;
