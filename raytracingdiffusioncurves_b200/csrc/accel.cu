@@ -307,6 +307,9 @@ void destroy_scene(rdc_scene* s) {
   cudaFree(s->frame_image);
   cudaFree(s->frame_scratch);
   cudaFree(s->frame_sigma);
+  cudaFree(s->part_rgbw);
+  cudaFree(s->part_blur);
+  cudaFree(s->tile_arrivals);
   cudaSetDevice(prev);
   delete s;
 }

@@ -84,6 +84,11 @@ struct rdc_scene {
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
   unsigned int* work_counters = nullptr;  // k_render's tile counter pair (one render in flight per handle)
   uint32_t grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // SM-filling grid size per kernel variant
+  // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
+  float4* part_rgbw = nullptr;
+  float* part_blur = nullptr;
+  unsigned int* tile_arrivals = nullptr;
+  size_t part_capacity = 0, tile_capacity = 0;
   // frame buffers of rdc_render_frame_to_host, grown on demand and kept (no per-frame allocation)
   float4* frame_image = nullptr;
   float4* frame_scratch = nullptr;

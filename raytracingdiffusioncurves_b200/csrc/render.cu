@@ -23,9 +23,8 @@ namespace rdc {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a big work unit: 8x4 pixels, one lane per pixel
-constexpr int kPhases = 4;                      // a small work unit: 8x1 pixels, kPhases lanes per pixel, lane q
-                                                // of a pixel tracing rays i = q (mod kPhases)
+constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a tile: 8x4 pixels, one lane per pixel, all lanes on the same ray index
+constexpr int kMaxSplit = 4;                    // a tile's rays may be dealt to up to 4 work units (rdc_scene::split)
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
@@ -44,7 +43,10 @@ struct RenderArgs {
   uint32_t width, height, row_begin, row_end;
   uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kStripRows: strip t belongs to t % stride == offset
   uint32_t local_rows;                  // rows of the output buffers this launch covers
-  uint32_t big_rows;                    // rows [0,big_rows) go out as big units, the rest as small ones
+  uint32_t split;                       // work units per tile: unit q traces rays i = q (mod split)
+  float4* part_rgbw;                    // [split][local pixels] partial sums of units (split > 1)
+  float* part_blur;
+  unsigned int* tile_arrivals;          // [tiles] units of the tile that have finished (self-rewinding)
   unsigned int* work;                   // [0] next warp tile, [1] warps finished (self-rewinding)
   int n_iter;         // number of loop trips: ceil(number_of_rays_per_pixel)
   float n_rays;       // number_of_rays_per_pixel
@@ -382,34 +384,31 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   }
 
   // Persistent warps: every warp of the (SM-filling) grid keeps fetching work units from one global
-  // counter until the image is done. Units differ in cost by an order of magnitude (how many rays reach
-  // the scene, how deep they go). The bulk of the image goes out as 8x4-pixel units, one lane per pixel,
-  // all lanes on the same ray index — the most coherent mapping. A lane then runs N rays back to back,
-  // and a warp left alone with such a unit at the end of the frame would take ~0.4 ms at 1080p; so the
-  // last rows go out as 8x1-pixel units with kPhases lanes per pixel (N/kPhases rays per lane), whose
-  // partial sums are combined by shuffles in a fixed order.
+  // counter until the image is done. A tile is 8x4 pixels, one lane per pixel, all lanes on the same ray
+  // index — the most coherent mapping. Tiles differ in cost by an order of magnitude (how many rays reach
+  // the scene, how deep they go), and a lane that runs all N rays of a pixel back to back holds its warp
+  // for ~0.4 ms at 1080p/128 — far too coarse a grain to balance a 2.5 ms frame, let alone an eighth of it.
+  // So a tile's rays are dealt to `split` units (unit q takes rays i = q mod split); each unit leaves its
+  // partial sums in global memory and the last one to arrive adds them up in unit order 0..split-1, which
+  // makes the result independent of timing and of how the frame is divided among GPUs.
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
-  const uint32_t n_big = tiles_x * ((a.big_rows + kWarpTileH - 1) / kWarpTileH);
-  const uint32_t n_tiles = n_big + tiles_x * (a.local_rows - a.big_rows);
+  const uint32_t n_units = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH) * a.split;
+  const size_t part_stride = (size_t)a.local_rows * a.width;
   const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
   float sigma_max = 0.0f;
   Counters cnt;
   for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(a.work, 1u);
-    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-    if (tile >= n_tiles) break;
-    const bool big = tile < n_big;
-    const uint32_t unit = big ? tile : tile - n_big;
-    const int phases = big ? 1 : kPhases;
-    const uint32_t phase = big ? 0u : lane / kWarpTileW;
-    const uint32_t ix = (unit % tiles_x) * kWarpTileW + lane % kWarpTileW;
-    // row inside the output buffer (band- or strip-local)
-    const uint32_t ly = big ? (unit / tiles_x) * kWarpTileH + lane / kWarpTileW : a.big_rows + unit / tiles_x;
+    uint32_t unit = 0;
+    if (lane == 0) unit = atomicAdd(a.work, 1u);
+    unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
+    if (unit >= n_units) break;
+    const uint32_t tile = unit / a.split, q = unit % a.split;
+    const uint32_t ix = (tile % tiles_x) * kWarpTileW + lane % kWarpTileW;
+    const uint32_t ly = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local)
     // row of the full image: contiguous band, or strip (ly / 16) of this rank's interleaved share
     const uint32_t iy = a.row_begin + ((ly / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly % kStripRows;
-    const bool valid = ix < a.width && iy < a.row_end && (!big || ly < a.big_rows);
+    const bool valid = ix < a.width && iy < a.row_end;
     const size_t local_pixel = (size_t)ly * a.width + ix;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
     if (valid) {
@@ -418,52 +417,82 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
                                    : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
       const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
+      // Ray indices that can reach the scene: [lo0,hi0] and (when the angular range wraps) [lo1,hi1],
+      // visited in ascending order like the reference's loop. Everything else is a miss and adds nothing.
+      int lo0 = 0, hi0 = a.n_iter - 1, lo1 = 1, hi1 = 0;
       int cull_first = 0, cull_span = 0;
-      const bool culling = pixel_cull(a, base_x, base_y, cull_first, cull_span);
-      for (int i = (int)phase; i < a.n_iter; i += phases) {
-        if (culling) {
-          int rel = i - cull_first;
-          if (rel < 0) rel += a.n_iter;
-          if (rel > cull_span) {  // cannot reach the scene: a miss, adds nothing
-            if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
-            continue;
+      if (pixel_cull(a, base_x, base_y, cull_first, cull_span)) {
+        if (a.hit_ids)  // parity runs record every ray: mark the culled ones
+          for (int i = (int)q; i < a.n_iter; i += (int)a.split) {
+            int rel = i - cull_first;
+            if (rel < 0) rel += a.n_iter;
+            if (rel > cull_span) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
+          }
+        const int last = cull_first + cull_span;
+        if (last < a.n_iter) {
+          lo0 = cull_first; hi0 = last;
+        } else {  // wraps past ray N-1
+          lo0 = 0; hi0 = last - a.n_iter;
+          lo1 = cull_first; hi1 = a.n_iter - 1;
+        }
+      }
+      for (int part = 0; part < 2; ++part) {
+        const int lo = part ? lo1 : lo0, hi = part ? hi1 : hi0;
+        // first index >= lo that belongs to this unit
+        int i = lo + (int)((q + a.split - (uint32_t)lo % a.split) % a.split);
+        for (; i <= hi; i += (int)a.split) {
+          const float2 base = __ldg(a.base_dirs + i);
+          // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
+          const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
+          float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
+          if (a.use_aa) {
+            float js, jc;
+            const float ang = a.two_over_n * rdc_u01(rnd.x);
+            if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
+            else rdc_sincospi(ang, &js, &jc);
+            dx = base.x * jc - base.y * js;
+            dy = base.x * js + base.y * jc;
+            ox = base_x + rdc_u01(rnd.y) * a.zoom;
+            oy = base_y + rdc_u01(rnd.z) * a.zoom;
+          }
+          uint32_t first_hit;
+          Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
+          if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
+          weight_total += s.w;
+          cr += s.r * s.w;
+          cg += s.g * s.w;
+          cb += s.b * s.w;
+          blur += s.blur * s.w;
+        }
+      }
+    }
+    bool finish = true;
+    if (a.split > 1) {
+      if (valid) {
+        a.part_rgbw[q * part_stride + local_pixel] = make_float4(cr, cg, cb, weight_total);
+        a.part_blur[q * part_stride + local_pixel] = blur;
+      }
+      __threadfence();
+      unsigned int arrived = 0;
+      if (lane == 0) arrived = atomicAdd(a.tile_arrivals + tile, 1u);
+      arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+      finish = arrived == a.split - 1;
+      if (finish) {
+        __threadfence();
+        if (lane == 0) a.tile_arrivals[tile] = 0u;  // rewound for the next frame
+        if (valid) {
+          const float4 p0 = __ldcg(a.part_rgbw + local_pixel);
+          cr = p0.x; cg = p0.y; cb = p0.z; weight_total = p0.w;
+          blur = __ldcg(a.part_blur + local_pixel);
+          for (uint32_t k = 1; k < a.split; ++k) {
+            const float4 pk = __ldcg(a.part_rgbw + k * part_stride + local_pixel);
+            cr += pk.x; cg += pk.y; cb += pk.z; weight_total += pk.w;
+            blur += __ldcg(a.part_blur + k * part_stride + local_pixel);
           }
         }
-        const float2 base = __ldg(a.base_dirs + i);
-        // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
-        const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
-        float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
-        if (a.use_aa) {
-          float js, jc;
-          const float ang = a.two_over_n * rdc_u01(rnd.x);
-          if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
-          else rdc_sincospi(ang, &js, &jc);
-          dx = base.x * jc - base.y * js;
-          dy = base.x * js + base.y * jc;
-          ox = base_x + rdc_u01(rnd.y) * a.zoom;
-          oy = base_y + rdc_u01(rnd.z) * a.zoom;
-        }
-        uint32_t first_hit;
-        Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
-        if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
-        weight_total += s.w;
-        cr += s.r * s.w;
-        cg += s.g * s.w;
-        cb += s.b * s.w;
-        blur += s.blur * s.w;
       }
     }
-    if (!big) {  // the pixel's kPhases partial sums, combined in a fixed (butterfly) order
-#pragma unroll
-      for (int m = kWarpTileW; m < 32; m <<= 1) {
-        weight_total += __shfl_xor_sync(0xFFFFFFFFu, weight_total, m);
-        cr += __shfl_xor_sync(0xFFFFFFFFu, cr, m);
-        cg += __shfl_xor_sync(0xFFFFFFFFu, cg, m);
-        cb += __shfl_xor_sync(0xFFFFFFFFu, cb, m);
-        blur += __shfl_xor_sync(0xFFFFFFFFu, blur, m);
-      }
-    }
-    if (valid && phase == 0) {
+    if (finish && valid) {
       // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
       a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
       const float sigma = blur / weight_total;
@@ -596,30 +625,33 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     }
     s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
   }
-  // Rows that go out as small units: about 1.5 big units' worth of pixels per resident warp, at most half
-  // the image. Which rows are "last" is fixed by the image size and the split alone, so a pixel's value does
-  // not depend on the GPU it runs on... but it does depend on the unit kind (summation order), hence the
-  // boundary is derived from the FULL image height: a row is small in every split or in none.
+  // Units per tile. It must not depend on how the frame is divided among GPUs (the summation order is part of
+  // the result), so it is a function of the full frame only: as many as kMaxSplit while each unit keeps at
+  // least 16 rays and the partial sums of the whole frame fit 2 GiB.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
-  const uint64_t resident_warps = (uint64_t)s->grid_blocks[variant] * (kBlock / 32);
-  uint64_t small_pixels = resident_warps * 48;
-  const uint64_t frame_pixels = (uint64_t)p.image_width * p.image_height;
-  if (small_pixels > frame_pixels / 2) small_pixels = frame_pixels / 2;
-  uint32_t small_rows_global = (uint32_t)((small_pixels + p.image_width - 1) / p.image_width);
-  small_rows_global = (small_rows_global + kStripRows - 1) / kStripRows * kStripRows;  // whole strips
-  const uint32_t big_limit_global = p.image_height > small_rows_global ? (p.image_height - small_rows_global) / kStripRows * kStripRows : 0;
-  // local rows whose global row is below big_limit_global
-  uint32_t big_rows = 0;
-  if (a.strip_stride > 1) {
-    const uint32_t big_strips_global = big_limit_global / kStripRows;  // strips [0, big_strips_global) are big
-    const uint32_t mine = a.strip_offset < big_strips_global ? (big_strips_global - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
-    big_rows = mine * kStripRows;
-  } else {
-    big_rows = big_limit_global > p.row_begin ? big_limit_global - p.row_begin : 0;
+  uint32_t split = kMaxSplit;
+  while (split > 1 && ((uint32_t)n_iter < 16 * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
+  a.split = split;
+  const size_t local_pixels = (size_t)a.local_rows * p.image_width;
+  const uint32_t local_tiles = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  if (split > 1 && (local_pixels * split > s->part_capacity || local_tiles > s->tile_capacity)) {
+    RDC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(s->part_rgbw);
+    cudaFree(s->part_blur);
+    cudaFree(s->tile_arrivals);
+    s->part_rgbw = nullptr; s->part_blur = nullptr; s->tile_arrivals = nullptr;
+    s->part_capacity = 0; s->tile_capacity = 0;
+    RDC_CUDA(cudaMalloc((void**)&s->part_rgbw, local_pixels * split * sizeof(float4)));
+    RDC_CUDA(cudaMalloc((void**)&s->part_blur, local_pixels * split * sizeof(float)));
+    RDC_CUDA(cudaMalloc((void**)&s->tile_arrivals, local_tiles * sizeof(unsigned int)));
+    RDC_CUDA(cudaMemsetAsync(s->tile_arrivals, 0, local_tiles * sizeof(unsigned int), stream));
+    s->part_capacity = local_pixels * split;
+    s->tile_capacity = local_tiles;
   }
-  if (big_rows > a.local_rows) big_rows = a.local_rows;
-  a.big_rows = big_rows;
-  const uint32_t warp_tiles = tiles_x * ((big_rows + kWarpTileH - 1) / kWarpTileH) + tiles_x * (a.local_rows - big_rows);
+  a.part_rgbw = s->part_rgbw;
+  a.part_blur = s->part_blur;
+  a.tile_arrivals = s->tile_arrivals;
+  const uint32_t warp_tiles = local_tiles * split;
   uint32_t grid = s->grid_blocks[variant];
   const uint32_t needed = (warp_tiles + kBlock / 32 - 1) / (kBlock / 32);
   if (grid > needed) grid = needed;
