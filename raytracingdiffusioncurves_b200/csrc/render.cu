@@ -319,6 +319,25 @@ __global__ void k_base_dirs(float2* out, int n_iter, float two_over_n) {
   }
 }
 
+// atan2 to within 1e-4 rad (odd polynomial on [0,1], |error| < 2e-5, plus the approximate reciprocal): only
+// used to bound an angular interval that is then widened by far more than that.
+__device__ __forceinline__ float atan2_bound(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(hi, 1e-30f)));
+  const float t = lo * inv, t2 = t * t;
+  float r = fmaf(t2, -0.0134804700f, 0.0574773140f);
+  r = fmaf(r, t2, -0.1212390710f);
+  r = fmaf(r, t2, 0.1956359250f);
+  r = fmaf(r, t2, -0.3329945970f);
+  r = fmaf(r, t2, 0.9999956300f);
+  r *= t;
+  if (ay > ax) r = 1.5707963267948966f - r;
+  if (x < 0.0f) r = 3.141592653589793f - r;
+  return y < 0.0f ? -r : r;
+}
+
 // Which rays of this pixel can reach the scene at all? Ray i leaves a point of the pixel's jitter square
 // [bx,bx+zoom]x[by,by+zoom] in a direction whose angle lies in stratum (i, i+1]*2pi/N (base direction i
 // plus a jitter of at most one stratum). Seen from any point of the square, the scene's padded box lies
@@ -341,14 +360,15 @@ __device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float 
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const float px = (c & 1) ? x1 : x0, py = (c & 2) ? y1 : y0;
-    const float d = atan2f(cx * py - cy * px, cx * px + cy * py);  // signed angle from the centre direction
+    const float d = atan2_bound(cx * py - cy * px, cx * px + cy * py);  // signed angle from the centre direction
     dmin = fminf(dmin, d);
     dmax = fmaxf(dmax, d);
   }
-  const float centre = atan2f(cy, cx);
+  const float centre = atan2_bound(cy, cx);
   const float strata_per_rad = (float)n * 0.15915494309189535f;
-  // safety: half a stratum plus the drift of the iterated rotation (n steps of ~1e-7 rad, in strata)
-  const float safety = 0.5f + 4e-8f * (float)n * (float)n;
+  // safety: half a stratum, the drift of the iterated rotation (n steps of ~1e-7 rad, in strata) and the
+  // error of atan2_bound (two of them meet in every interval end: 1e-3 rad covers it ten times over)
+  const float safety = 0.5f + 4e-8f * (float)n * (float)n + 1e-3f * strata_per_rad;
   const float lo = (centre + dmin) * strata_per_rad - 1.0f - safety;  // ray i reaches up to stratum end i+1
   const float hi = (centre + dmax) * strata_per_rad + safety;
   const int ilo = (int)floorf(lo), ihi = (int)ceilf(hi);
