@@ -15,6 +15,7 @@
 //   * tree culling only uses conservative box tests; the accepted hit is the lexicographic minimum of
 //     (t, chord id) over all chords, the same rule the brute-force oracle applies.
 #include <cstdio>
+#include <cstdlib>
 
 #include "device_scene.h"
 #include "rdc_math.h"
@@ -650,6 +651,10 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   // least 16 rays and the partial sums of the whole frame fit 2 GiB.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
   uint32_t split = kMaxSplit;
+  if (const char* env = getenv("RDC_B200_SPLIT")) {  // tuning experiments only
+    int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4) split = (uint32_t)v;
+  }
   while (split > 1 && ((uint32_t)n_iter < 16 * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
   a.split = split;
   const size_t local_pixels = (size_t)a.local_rows * p.image_width;
