@@ -152,10 +152,17 @@ RDC_HD float rdc_ratio(float num, float den) {
 
 // walk from `first` (any index the walk from the list's start is known to reach) up to `end` = start+count
 RDC_HD int rdc_interp_from(uint32_t first, uint32_t end, float u, const float* us, float* ratio) {
-  int ind = (int)first;
-  while ((uint32_t)ind < end && us[ind + 1] < u) ind++;
-  *ratio = rdc_ratio(u - us[ind], us[ind + 1] - us[ind]);
-  return ind;
+  // same walk as DeviceCode.cu:39-43, carrying us[ind] and us[ind+1] in registers: one load per step
+  const float* p = us + first;
+  const float* const stop = us + end;
+  float lo = p[0], hi = p[1];
+  while (p < stop && hi < u) {
+    ++p;
+    lo = hi;
+    hi = p[1];
+  }
+  *ratio = rdc_ratio(u - lo, hi - lo);
+  return (int)(p - us);
 }
 
 RDC_HD int rdc_interp(uint32_t start, uint32_t count, float u, const float* us, float* ratio) {
