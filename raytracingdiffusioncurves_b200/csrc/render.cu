@@ -90,42 +90,57 @@ __device__ __forceinline__ float slab_rcp(float d) {
 }
 
 // All chords of one run against the ray. Edge values of the shared end points are computed once; the
-// record is read two points at a time and only as far as the run is long.
+// record is read two points at a time and only as far as the run is long. The unrolled pass only marks
+// the chords whose end points lie on different sides of the ray; the (rare) marked ones are then resolved
+// in a rolled loop that re-reads their two points — same inputs, same operations, same bits.
 template <bool SMEM, bool PORTALS>
 __device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
                                          uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
   const float4* rp = ac.runs + (size_t)leaf * kRunVec;
   const float4 head = load16<SMEM>(rp);
-  const uint32_t first_id = __float_as_uint(head.x);
   const int count = (int)__float_as_uint(head.y);
-  float wax = head.z - ox, way = head.w - oy;
-  float ea = rdc_edge(dx, dy, wax, way);
+  bool prev = rdc_edge(dx, dy, head.z - ox, head.w - oy) > 0.0f;
+  uint32_t crossed = 0;
 #pragma unroll
   for (int v = 1; v < kRunVec; ++v) {
     if (2 * v - 2 >= count) break;
     const float4 q = load16<SMEM>(rp + v);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int j = 2 * v - 2 + half;
-      const float wbx = (half ? q.z : q.x) - ox, wby = (half ? q.w : q.y) - oy;
-      const float eb = rdc_edge(dx, dy, wbx, wby);
-      if (j < count && (ea > 0.0f) != (eb > 0.0f)) {
-        float t, s;
-        if (rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, ea, eb, &t, &s)) {
-          const uint32_t id = first_id + (uint32_t)j;
-          if (!(PORTALS && id >= skip_lo && id <= skip_hi) && rdc_hit_closer(t, id, h.t, h.id)) {
-            h.t = t; h.s = s; h.leaf = leaf; h.j = j; h.id = id;
-          }
-        }
+    const bool s0 = rdc_edge(dx, dy, q.x - ox, q.y - oy) > 0.0f;
+    const bool s1 = rdc_edge(dx, dy, q.z - ox, q.w - oy) > 0.0f;
+    if (s0 != prev) crossed |= 1u << (2 * v - 2);
+    if (s1 != s0 && 2 * v - 1 < count) crossed |= 1u << (2 * v - 1);
+    prev = s1;
+  }
+  if (crossed == 0) return;
+  const uint32_t first_id = __float_as_uint(head.x);
+  const float2* pts = reinterpret_cast<const float2*>(rp) + 1;  // P0 follows the two header words
+  while (crossed) {
+    const int j = __ffs(crossed) - 1;
+    crossed &= crossed - 1;
+    const float2 pa = SMEM ? pts[j] : __ldg(pts + j), pb = SMEM ? pts[j + 1] : __ldg(pts + j + 1);
+    const float wax = pa.x - ox, way = pa.y - oy, wbx = pb.x - ox, wby = pb.y - oy;
+    float t, s;
+    if (rdc_chord_hit(dx, dy, inv_dd, wax, way, wbx, wby, rdc_edge(dx, dy, wax, way), rdc_edge(dx, dy, wbx, wby), &t, &s)) {
+      const uint32_t id = first_id + (uint32_t)j;
+      if (!(PORTALS && id >= skip_lo && id <= skip_hi) && rdc_hit_closer(t, id, h.t, h.id)) {
+        h.t = t; h.s = s; h.leaf = leaf; h.j = j; h.id = id;
       }
-      wax = wbx; way = wby; ea = eb;
     }
   }
 }
 
+// Every run against the ray: the kernel behind RDC_TRAVERSAL_BRUTE_FORCE (validation only, kept out of line).
+template <bool SMEM, bool PORTALS>
+__device__ __noinline__ void brute_force(const Accel& ac, float ox, float oy, float dx, float dy, float inv_dd,
+                                         uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
+  for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+}
+
 // Closest chord along the ray. Ordered depth-first traversal: the nearer child first, the farther one on
-// a per-thread stack; a child is entered when the ray's interval inside its box starts before the best
-// hit so far (with RDC_CULL_SLACK). Leaves are tested as soon as their box is hit.
+// a per-thread stack together with its entry distance, so that a subtree that lies behind a hit found in
+// the meantime is dropped when it is popped, without fetching it. A child is entered when the ray's
+// interval inside its box starts before the best hit so far (with RDC_CULL_SLACK). Leaves go through the
+// same loop (one leaf-test site keeps the kernel inside the instruction cache).
 template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
                                              bool primary, uint32_t skip_lo, uint32_t skip_hi, Counters& cnt) {
@@ -138,53 +153,51 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   h.id = kMiss;
   const float inv_dd = PORTALS ? rdc_inv_dd(dx, dy, primary) : 1.0f;
   if (brute) {
-    for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+    brute_force<SMEM, PORTALS>(ac, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
     if (STATS) cnt.chords += ac.n_runs * RDC_RUN;
     return h;
   }
   const float idx = slab_rcp(dx), idy = slab_rcp(dy);
-  int stack[kStack];
+  int2 stack[kStack];  // (node, entry distance bits)
   int sp = 0;
   int node = 0;
   for (;;) {
-    if (STATS) cnt.nodes++;
-    const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
-    float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
-    float4 ch = load16<SMEM>(np + 2);
-    int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
-    float le, re;
-    float ln = rdc_slab(ox, oy, idx, idy, lb.x, lb.y, lb.z, lb.w, &le);
-    float rn = rdc_slab(ox, oy, idx, idy, rb.x, rb.y, rb.z, rb.w, &re);
-    float lim = h.t * RDC_CULL_SLACK;
-    bool hl = ln <= le && ln <= lim;
-    bool hr = rn <= re && rn <= lim;
-    if (hl && left < 0) {
+    if (node < 0) {
       if (STATS) cnt.chords += RDC_RUN;
-      test_run<SMEM, PORTALS>(ac, ~left, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
-      hl = false;
-    }
-    if (hr && right < 0) {
-      // the left leaf may just have shortened the ray
-      if (rn <= h.t * RDC_CULL_SLACK) {
-        if (STATS) cnt.chords += RDC_RUN;
-        test_run<SMEM, PORTALS>(ac, ~right, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
-      }
-      hr = false;
-    }
-    if (hl && hr) {
-      bool left_first = ln <= rn;
-      stack[sp++] = left_first ? right : left;
-      node = left_first ? left : right;
-    } else if (hl) {
-      node = left;
-    } else if (hr) {
-      node = right;
+      test_run<SMEM, PORTALS>(ac, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
     } else {
-      if (sp == 0) break;
-      node = stack[--sp];
+      if (STATS) cnt.nodes++;
+      const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
+      const float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
+      const float4 ch = load16<SMEM>(np + 2);
+      const int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+      float le, re;
+      const float ln = rdc_slab(ox, oy, idx, idy, lb.x, lb.y, lb.z, lb.w, &le);
+      const float rn = rdc_slab(ox, oy, idx, idy, rb.x, rb.y, rb.z, rb.w, &re);
+      const float lim = h.t * RDC_CULL_SLACK;
+      const bool hl = ln <= le && ln <= lim;
+      const bool hr = rn <= re && rn <= lim;
+      if (hl && hr) {
+        const bool left_first = ln <= rn;
+        stack[sp++] = make_int2(left_first ? right : left, __float_as_int(left_first ? rn : ln));
+        node = left_first ? left : right;
+        continue;
+      }
+      if (hl || hr) {
+        node = hl ? left : right;
+        continue;
+      }
+    }
+    // pop the nearest pending subtree that still starts before the best hit
+    for (;;) {
+      if (sp == 0) return h;
+      const int2 e = stack[--sp];
+      if (__int_as_float(e.y) <= h.t * RDC_CULL_SLACK) {
+        node = e.x;
+        break;
+      }
     }
   }
-  return h;
 }
 
 __device__ __forceinline__ void load_control_points(const DevScene& sc, uint32_t seg, rdc_f2 v[4]) {
@@ -319,6 +332,9 @@ __global__ void k_base_dirs(float2* out, int n_iter, float two_over_n) {
     x = nx; y = ny;
   }
 }
+
+// fewer than 8 rays per pixel: the jitter angle needs the range reduction (cold path, kept out of line)
+__device__ __noinline__ void sincospi_general(float x, float* s, float* c) { rdc_sincospi(x, s, c); }
 
 // atan2 to within 1e-4 rad (odd polynomial on [0,1], |error| < 2e-5, plus the approximate reciprocal): only
 // used to bound an angular interval that is then widened by far more than that.
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
             float js, jc;
             const float ang = a.two_over_n * rdc_u01(rnd.x);
             if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
-            else rdc_sincospi(ang, &js, &jc);
+            else sincospi_general(ang, &js, &jc);
             dx = base.x * jc - base.y * js;
             dy = base.x * js + base.y * jc;
             ox = base_x + rdc_u01(rnd.y) * a.zoom;
