@@ -410,7 +410,10 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     const uint32_t run_words = a.sc.n_runs * (uint32_t)kRunVec;
     const uint4* gn = reinterpret_cast<const uint4*>(a.sc.nodes);
     const uint4* gr = reinterpret_cast<const uint4*>(a.sc.runs);
+    // once per persistent block: keep these loops rolled, the kernel has to fit the instruction cache
+#pragma unroll 1
     for (uint32_t i = threadIdx.x; i < node_words; i += kBlock) smem[i] = __ldg(gn + i);
+#pragma unroll 1
     for (uint32_t i = threadIdx.x; i < run_words; i += kBlock) smem[node_words + i] = __ldg(gr + i);
     __syncthreads();
     ac.nodes = reinterpret_cast<const BvhNode*>(smem);
@@ -460,6 +463,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       int cull_first = 0, cull_span = 0;
       if (pixel_cull(a, base_x, base_y, cull_first, cull_span)) {
         if (a.hit_ids)  // parity runs record every ray: mark the culled ones
+#pragma unroll 1
           for (int i = (int)q; i < a.n_iter; i += (int)a.split) {
             int rel = i - cull_first;
             if (rel < 0) rel += a.n_iter;
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           lo1 = cull_first; hi1 = a.n_iter - 1;
         }
       }
+#pragma unroll 1
       for (int part = 0; part < 2; ++part) {
         const int lo = part ? lo1 : lo0, hi = part ? hi1 : hi0;
         // first index >= lo that belongs to this unit
@@ -521,6 +526,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           const float4 p0 = __ldcg(a.part_rgbw + local_pixel);
           cr = p0.x; cg = p0.y; cb = p0.z; weight_total = p0.w;
           blur = __ldcg(a.part_blur + local_pixel);
+#pragma unroll 1
           for (uint32_t k = 1; k < a.split; ++k) {
             const float4 pk = __ldcg(a.part_rgbw + k * part_stride + local_pixel);
             cr += pk.x; cg += pk.y; cb += pk.z; weight_total += pk.w;
