@@ -84,8 +84,6 @@ typedef struct rdc_scene_info {
   uint64_t device_bytes;    /* everything the handle owns on the device            */
   uint64_t traversal_bytes; /* nodes + leaf runs: what a ray touches                */
   float pad;                /* box padding actually used                           */
-  int tree_kind;            /* 0 = radix tree (Karras), 1 = median tree: whichever costs less */
-  float tree_cost_radix, tree_cost_median; /* sum of child-box perimeters */
 } rdc_scene_info;
 
 void rdc_default_accel_options(rdc_accel_options* opts);

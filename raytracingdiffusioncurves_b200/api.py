@@ -57,8 +57,7 @@ class SceneInfo(C.Structure):
     _fields_ = [
         ("n_segments", C.c_uint32), ("n_curves", C.c_uint32), ("n_chords", C.c_uint32), ("n_runs", C.c_uint32),
         ("n_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("has_portals", C.c_int), ("device_bytes", C.c_uint64),
-        ("traversal_bytes", C.c_uint64), ("pad", C.c_float), ("tree_kind", C.c_int), ("tree_cost_radix", C.c_float),
-        ("tree_cost_median", C.c_float),
+        ("traversal_bytes", C.c_uint64), ("pad", C.c_float),
     ]
 
 
@@ -265,9 +264,6 @@ class SceneStats:
     device_bytes: int
     traversal_bytes: int
     pad: float
-    tree_kind: int = 0
-    tree_cost_radix: float = 0.0
-    tree_cost_median: float = 0.0
 
 
 class Scene:
@@ -281,8 +277,7 @@ class Scene:
         info = SceneInfo()
         _check(_lib.rdc_scene_get_info(self._h, C.byref(info)), "rdc_scene_get_info")
         self.stats = SceneStats(info.n_segments, info.n_curves, info.n_chords, info.n_runs, info.n_nodes, info.bvh_depth,
-                                bool(info.has_portals), info.device_bytes, info.traversal_bytes, info.pad, info.tree_kind,
-                                info.tree_cost_radix, info.tree_cost_median)
+                                bool(info.has_portals), info.device_bytes, info.traversal_bytes, info.pad)
 
     @property
     def handle(self) -> C.c_void_p:

@@ -17,7 +17,6 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -209,42 +208,6 @@ __global__ void k_radix_tree(const uint32_t* codes, int n, BvhNode* nodes, int* 
   if (i == 0) nodes[i].parent = -1;
   if (left < 0) leaf_parent[gamma] = i; else nodes[left].parent = i;
   if (right < 0) leaf_parent[gamma + 1] = i; else nodes[right].parent = i;
-}
-
-// Alternative hierarchy over the same Morton-ordered leaves: every range is cut in the middle, so the depth
-// is ceil(log2 n). The inner node that cuts between leaves g and g+1 gets index g (each gap is cut exactly
-// once), which lets one thread per node find its own range by walking down from the root range.
-__global__ void k_median_tree(int n, BvhNode* nodes, int* leaf_parent) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n - 1) return;
-  int lo = 0, hi = n - 1, parent = -1;
-  for (;;) {
-    const int mid = (lo + hi) >> 1;
-    if (mid == g) break;
-    parent = mid;
-    if (g < mid) hi = mid; else lo = mid + 1;
-  }
-  const int mid = g;
-  const int left = (lo == mid) ? ~lo : ((lo + mid) >> 1);
-  const int right = (mid + 1 == hi) ? ~hi : ((mid + 1 + hi) >> 1);
-  nodes[g].left = left;
-  nodes[g].right = right;
-  nodes[g].parent = parent;
-  nodes[g].pad = 0;
-  if (left < 0) leaf_parent[lo] = g;
-  if (right < 0) leaf_parent[hi] = g;
-}
-
-// Expected number of box tests of a random line ~ sum of the perimeters of all child boxes.
-__global__ void k_tree_cost(const BvhNode* nodes, int n_nodes, float* cost) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float c = 0.0f;
-  if (i < n_nodes) {
-    const float4 l = nodes[i].lbox, r = nodes[i].rbox;
-    c = fmaxf(l.z - l.x, 0.0f) + fmaxf(l.w - l.y, 0.0f) + fmaxf(r.z - r.x, 0.0f) + fmaxf(r.w - r.y, 0.0f);
-  }
-  for (int m = 16; m > 0; m >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, m);
-  if ((threadIdx.x & 31) == 0 && c > 0.0f) atomicAdd(cost, c);
 }
 
 __device__ __forceinline__ float4 padded(float4 b, float pad) {
@@ -579,73 +542,22 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   k_gather_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(order, runs_in, ids_in, box_in, n_runs, runs, run_ids, leaf_box);
   TEMP_CUDA(cudaGetLastError());
 
-  // Two hierarchies over the same sorted leaves — the radix tree (cuts where the Morton codes differ) and the
-  // median tree (cuts every range in the middle) — are fitted; the one whose boxes a random line crosses
-  // less often is kept. Curves are nearly one-dimensional sets: on small scenes the radix tree is lopsided
-  // (16 leaves, depth 6 on arch.xml) and the median tree wins; on dense scenes the radix tree separates better.
-  BvhNode* alt_nodes = nullptr;
-  float* costs = nullptr;        // [2] radix, median
-  unsigned int* depths = nullptr;  // [2]
-  auto free_alt = [&]() { cudaFree(alt_nodes); cudaFree(costs); cudaFree(depths); };
-  uint32_t root = 0;
-  unsigned int depth = 0;
+  TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
   if (n_runs == 1) {
     k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_box, pad, nodes);
     TEMP_CUDA(cudaGetLastError());
-    TEMP_CUDA(cudaStreamSynchronize(stream));
-    depth = 1;
   } else {
-#define ALT_CUDA(call)                                          \
-  do {                                                          \
-    cudaError_t e__ = (call);                                   \
-    if (e__ != cudaSuccess) {                                   \
-      free_alt();                                               \
-      free_temps();                                             \
-      return fail(cuda_fail(e__, #call));                       \
-    }                                                           \
-  } while (0)
-    ALT_CUDA(cudaMalloc(&alt_nodes, n_nodes * sizeof(BvhNode)));
-    ALT_CUDA(cudaMalloc(&costs, 2 * sizeof(float)));
-    ALT_CUDA(cudaMalloc(&depths, 2 * sizeof(unsigned int)));
-    ALT_CUDA(cudaMemsetAsync(costs, 0, 2 * sizeof(float), stream));
-    ALT_CUDA(cudaMemsetAsync(depths, 0, 2 * sizeof(unsigned int), stream));
-    for (int which = 0; which < 2; ++which) {
-      BvhNode* tree = which == 0 ? nodes : alt_nodes;
-      ALT_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
-      if (which == 0) k_radix_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>(codes, (int)n_runs, tree, leaf_parent);
-      else k_median_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>((int)n_runs, tree, leaf_parent);
-      ALT_CUDA(cudaGetLastError());
-      k_fit_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, (int)n_runs, pad, leaf_parent, tree, node_box, arrivals);
-      ALT_CUDA(cudaGetLastError());
-      k_depth<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_parent, tree, (int)n_runs, depths + which);
-      ALT_CUDA(cudaGetLastError());
-      k_tree_cost<<<blocks_for(n_nodes), kThreads, 0, stream>>>(tree, (int)n_nodes, costs + which);
-      ALT_CUDA(cudaGetLastError());
-    }
-    float h_cost[2] = {0, 0};
-    unsigned int h_depth[2] = {0, 0};
-    ALT_CUDA(cudaMemcpyAsync(h_cost, costs, sizeof h_cost, cudaMemcpyDeviceToHost, stream));
-    ALT_CUDA(cudaMemcpyAsync(h_depth, depths, sizeof h_depth, cudaMemcpyDeviceToHost, stream));
-    ALT_CUDA(cudaStreamSynchronize(stream));
-    int pick = (h_cost[1] < h_cost[0]) ? 1 : 0;
-    if (const char* env = getenv("RDC_B200_TREE")) {  // tuning experiments only: "radix" or "median"
-      if (env[0] == 'r') pick = 0;
-      if (env[0] == 'm') pick = 1;
-    }
-    if (h_depth[pick] > 62) pick = 1;  // the median tree never exceeds ceil(log2 n)
-    if (pick == 1) {
-      ALT_CUDA(cudaMemcpyAsync(nodes, alt_nodes, n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToDevice, stream));
-      ALT_CUDA(cudaStreamSynchronize(stream));
-      root = (n_runs - 1) / 2;
-    }
-    depth = h_depth[pick];
-    s->info.tree_kind = pick;
-    s->info.tree_cost_radix = h_cost[0];
-    s->info.tree_cost_median = h_cost[1];
-    free_alt();
-#undef ALT_CUDA
+    TEMP_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
+    k_radix_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>(codes, (int)n_runs, nodes, leaf_parent);
+    TEMP_CUDA(cudaGetLastError());
+    k_fit_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, (int)n_runs, pad, leaf_parent, nodes, node_box, arrivals);
+    TEMP_CUDA(cudaGetLastError());
+    k_depth<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_runs, max_depth);
+    TEMP_CUDA(cudaGetLastError());
   }
-  (void)max_depth;
+  unsigned int depth = 0;
+  TEMP_CUDA(cudaMemcpyAsync(&depth, max_depth, sizeof depth, cudaMemcpyDeviceToHost, stream));
+  TEMP_CUDA(cudaStreamSynchronize(stream));
   free_temps();
   if (depth > 62) {
     set_error("accel: tree depth %u exceeds the traversal stack", depth);
@@ -662,7 +574,6 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   d.n_chords = n_chords;
   d.n_runs = n_runs;
   d.n_nodes = n_nodes;
-  d.root = root;
   d.root_box = make_float4(hb.xmin - pad, hb.ymin - pad, hb.xmax + pad, hb.ymax + pad);
   s->info.n_segments = a.n_segments;
   s->info.n_curves = a.n_curves;

@@ -70,7 +70,6 @@ struct DevScene {
   const BvhNode* nodes;            // [max(n_runs-1,1)]
   float4 root_box;                 // padded box of the whole scene (per-pixel angular culling)
   uint32_t n_segments, n_curves, n_chords, n_runs, n_nodes;
-  uint32_t root;                   // index of the tree's root node
 };
 
 struct rdc_scene {

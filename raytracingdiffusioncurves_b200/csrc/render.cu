@@ -68,7 +68,6 @@ struct Accel {
   const BvhNode* nodes;
   const float4* runs;  // kRunVec float4 per run
   uint32_t n_runs;
-  int root;
 };
 
 // per-thread work counters of the counting build (rdc_frame_params::stats)
@@ -161,7 +160,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   const float idx = slab_rcp(dx), idy = slab_rcp(dy);
   int2 stack[kStack];  // (node, entry distance bits)
   int sp = 0;
-  int node = ac.root;
+  int node = 0;
   for (;;) {
     if (node < 0) {
       if (STATS) cnt.chords += RDC_RUN;
@@ -406,7 +405,6 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   extern __shared__ uint4 smem[];
   Accel ac;
   ac.n_runs = a.sc.n_runs;
-  ac.root = (int)a.sc.root;
   if (SMEM) {
     const uint32_t node_words = a.sc.n_nodes * (uint32_t)(sizeof(BvhNode) / 16);
     const uint32_t run_words = a.sc.n_runs * (uint32_t)kRunVec;

@@ -36,10 +36,7 @@ def main():
                           flag.data_ptr(), stream)
         t1.record()
         torch.cuda.synchronize()
-        st = scene.stats
-        print(f"frame {f}: {t0.elapsed_time(t1):.3f} ms, chords {st.n_chords}, runs {st.n_runs}, depth {st.bvh_depth}, "
-              f"tree {'median' if st.tree_kind else 'radix'} (cost radix {st.tree_cost_radix:.0f} median {st.tree_cost_median:.0f}), "
-              f"max sigma {flag.item():.3f}")
+        print(f"frame {f}: {t0.elapsed_time(t1):.3f} ms, chords {scene.stats.n_chords}, max sigma {flag.item():.3f}")
 
 
 if __name__ == "__main__":
