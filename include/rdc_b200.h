@@ -163,8 +163,18 @@ int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, i
 /* ---- output conventions of the F11 screenshot (glfw_events.cpp:73-94) ---- */
 /* float4 image -> RGBA8: min(v*255,255), NaN -> 0, rows flipped when flip != 0. Host memory. */
 int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint8_t* out);
-/* binary PPM (P6) writer for headless runs */
+/* binary PPM (P6) and PNG (RGBA, uncompressed deflate) writers for headless runs */
 int rdc_write_ppm(const char* path, const uint8_t* rgba, int width, int height);
+int rdc_write_png(const char* path, const uint8_t* rgba, int width, int height);
+
+/* ---- the steps either side of the path in the frame loop ---- */
+/* scroll_callback (glfw_events.cpp:105-112): zoom_factor *= 1.5^-yoffset */
+void rdc_view_scroll(rdc_frame_params* params, double yoffset);
+/* mouse_cursor_callback while dragging (glfw_events.cpp:115-130): offset -= cursor delta * zoom_factor */
+void rdc_view_drag(rdc_frame_params* params, double dx, double dy);
+/* Running mean over frames, in the role of the OptiX temporal denoiser the reference enables
+ * (optixHello.cpp:1186-1235): accum <- accum + (image - accum)/(frames_so_far + 1). float4 device buffers. */
+int rdc_accumulate(float* accum, const float* image, size_t n_pixels, uint32_t frames_so_far, rdc_stream stream);
 
 /* ---- synthetic scenes: n_curves single-segment curves, SplitMix64(seed),
  *      emitted as XML text in the reference's schema so it passes through the same loader.

@@ -101,6 +101,10 @@ PROTOTYPES = {
     "rdc_render_frame_to_host": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_void_p, C.c_void_p]),
     "rdc_image_to_rgba8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rdc_write_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "rdc_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "rdc_view_scroll": (None, [C.POINTER(FrameParams), C.c_double]),
+    "rdc_view_drag": (None, [C.POINTER(FrameParams), C.c_double, C.c_double]),
+    "rdc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "rdc_synth_xml": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rdc_microbench_fp32": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "rdc_last_error_string": (C.c_char_p, []),

@@ -55,3 +55,49 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r'#\s*include[^\n]*oracle|^\s*(from|import)\s+[^\n]*oracle|dlopen[^\n]*oracle|CDLL[^\n]*oracle',
                                      text, flags=re.M), f"{f} reaches into oracle/"
+
+
+def test_view_helpers_follow_the_glfw_callbacks():
+    p = api.default_frame_params(64, 64, 8)
+    api.lib.rdc_view_scroll(ctypes.byref(p), 1.0)          # glfw_events.cpp:110: zoom *= 1.5^-yoffset
+    assert abs(p.zoom_factor - 1 / 1.5) < 1e-7
+    api.lib.rdc_view_scroll(ctypes.byref(p), -2.0)
+    assert abs(p.zoom_factor - 1.5) < 1e-6
+    api.lib.rdc_view_drag(ctypes.byref(p), 10.0, -4.0)     # :121-122: offset -= delta * zoom
+    assert abs(p.offset_x + 15.0) < 1e-5 and abs(p.offset_y - 6.0) < 1e-5
+
+
+def test_png_writer_round_trips(tmp_path):
+    import struct
+    import zlib
+
+    import numpy as np
+
+    img = (np.arange(5 * 7 * 4) % 251).astype(np.uint8).reshape(5, 7, 4)
+    path = str(tmp_path / "x.png")
+    assert api.lib.rdc_write_png(path.encode(), img.ctypes.data, 7, 5) == 0
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        n, kind = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(kind + body)
+        if kind == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", body)
+        if kind == b"IDAT":
+            idat += body
+        pos += 12 + n
+    assert ihdr == (7, 5, 8, 6, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(5, 7 * 4 + 1)
+    assert np.all(raw[:, 0] == 0) and np.array_equal(raw[:, 1:].reshape(5, 7, 4), img)
+
+
+def test_optixhello_usage_message_and_exit_code():
+    """optixHello.cpp:83-86: fewer than two arguments -> this message, exit code 1 (no GPU needed)."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "raytracingdiffusioncurves_b200", "OptixHello")
+    r = subprocess.run([exe, "only_one_argument"], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert r.stdout.strip() == "Please provide a path to a diffusion curve xml and the number of rays per pixel"

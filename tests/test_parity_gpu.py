@@ -263,3 +263,32 @@ def test_synthetic_scene_global_memory_path(api, port_oracle, tmp_path):
     out = r.render(product_params(api, p), want_hits=True)
     assert np.array_equal(out["hits"], ohits)
     compare_images(out["image"], oimg, RGB_TOL)
+
+
+def test_accumulate_is_a_running_mean(api):
+    import torch
+
+    frames = [torch.rand((6, 5, 4), dtype=torch.float32, device="cuda") for _ in range(5)]
+    acc = torch.zeros_like(frames[0])
+    s = torch.cuda.current_stream().cuda_stream
+    for k, f in enumerate(frames):
+        assert api.lib.rdc_accumulate(acc.data_ptr(), f.data_ptr(), 30, k, s) == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(acc, torch.stack(frames).mean(0), atol=1e-6)
+
+
+def test_optixhello_cli_renders_and_reports(xml_dir, tmp_path):
+    """The reference's command line: positional xml (relative to the current directory) and rays per pixel;
+    'Setup took' and 'Average frame time' lines (optixHello.cpp:1157,1263)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "raytracingdiffusioncurves_b200", "OptixHello")
+    out = tmp_path / "arch.png"
+    r = subprocess.run([exe, "tests/golden/xmls/arch.xml", "16", "--width", "160", "--height", "120", "--frames", "2", "--out", str(out)],
+                       cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Setup took : " in r.stdout and "Average frame time  : " in r.stdout and "frame : 2" in r.stdout
+    assert out.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+    missing = subprocess.run([exe, "tests/golden/xmls/nope.xml", "16"], cwd=root, capture_output=True, text=True)
+    assert missing.returncode == 2 and "cannot open" in missing.stderr
