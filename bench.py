@@ -44,6 +44,12 @@ XML_DIR = os.path.join(ROOT, "tests", "golden", "xmls")
 # algorithmic work per ray, FMA = 2 flops
 F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
 
+# From the committed `ncu --set full` capture of k_render on the headline workload
+# (profiles/r01_k_render_v4_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
+NCU_CAPTURE = {
+    "arch_1080p_128rpp": {"dram_bytes": 5.218048e6 + 163.349248e6, "issue_active": 0.8269, "source": "profiles/r01_k_render_v4_ncu_summary.txt"},
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -388,13 +394,16 @@ def main():
         alg_bytes = float(my_rows) * width * 20.0
         roofline = {
             "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp32_peak, "traffic": None,
+            "frac": achieved / fp32_peak,
+            "traffic": NCU_CAPTURE.get(args.workload, {}).get("dram_bytes") if world == 1 else None,
+            "issue_slots": NCU_CAPTURE.get(args.workload) if world == 1 else None,
             "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
             "kernel_ms": kernel_ms, "flops_per_ray": f_ray,
             "per_ray": {"nodes": n_node, "chords": n_seg, "hits_shaded": n_hit, "rays_traced": traced / band_rays},
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
-                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound"},
+                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; measured DRAM traffic is ~4x that "
+                            "because the partial sums of split work units are written back (see DESIGN.md 3.1)"},
         }
 
     cpu_baseline = None
