@@ -3,8 +3,8 @@
 // Same result as helperKernels.cu:48-148 (gaussHorizontal, gaussVertical, gaussianBlur): taps
 // k in [-ceil(3 sigma), +ceil(3 sigma)], weight expf(-(k*k)/(sigma+1e-6)^2) (no factor 2), clamp-to-edge,
 // renormalised, all four channels, the vertical pass reads the SAME un-blurred sigma map.
-// What differs is the execution: one thread per pixel over the whole image instead of a fixed 512x256
-// grid-stride launch, accumulation in registers instead of read-modify-write on dest[i], scratch supplied
+// What differs is the execution: a grid sized to the GPU (148 SMs x 16 blocks) instead of a fixed 512x256
+// launch, accumulation in registers instead of read-modify-write on dest[i], scratch supplied
 // by the caller (or the stream-ordered allocator) instead of cudaMalloc/cudaFree per frame, and an
 // optional device flag that turns both passes into (at most) one copy when every sigma is zero.
 #include "device_scene.h"
@@ -13,6 +13,7 @@ namespace rdc {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr unsigned kMaxBlocks = 148 * 16;  // 148 SMs x 16 resident blocks of 256 threads at most
 constexpr float kMinSigma = 1e-6f;   // helperKernels.cu:27
 constexpr float kMaxTaps = 16384.0f; // |k| bound for non-finite or absurd sigmas (edge pixels repeat anyway)
 
@@ -47,55 +48,66 @@ __device__ __forceinline__ bool all_sigma_zero(const float* max_sigma) {
 // identity, so it writes `dest` directly (nothing at all when dest == source).
 __global__ void k_blur_horizontal(const float4* __restrict__ source, float4* scratch, float4* dest,
                                   const float* __restrict__ sigma, int width, int h_begin, int h_end, const float* max_sigma) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= (size_t)width * (h_end - h_begin)) return;
-  const size_t i = j + (size_t)h_begin * width;
-  if (all_sigma_zero(max_sigma)) {
-    if (dest != source) dest[i] = source[i];
-    return;
+  const size_t count = (size_t)width * (h_end - h_begin), first = (size_t)h_begin * width;
+  const size_t stride = (size_t)blockDim.x * gridDim.x;
+  const bool identity = all_sigma_zero(max_sigma);
+  if (identity && dest == source) return;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+    const size_t i = first + j;
+    if (identity) {
+      dest[i] = source[i];
+      continue;
+    }
+    const int x = (int)(i % width);
+    const size_t row = i - x;
+    const Taps t = taps_for(sigma[i]);
+    float accum = 0.0f;
+    float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int k = t.first; k <= t.last; ++k) {
+      const int sx = max(0, min(x + k, width - 1));
+      const float g = expf(-(k * k) / t.sig_square);
+      const float4 s = source[row + sx];
+      accum += g;
+      d.x += s.x * g;
+      d.y += s.y * g;
+      d.z += s.z * g;
+      d.w += s.w * g;
+    }
+    scratch[i] = make_float4(d.x / accum, d.y / accum, d.z / accum, d.w / accum);
   }
-  const int x = (int)(i % width);
-  const size_t row = i - x;
-  const Taps t = taps_for(sigma[i]);
-  float accum = 0.0f;
-  float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  for (int k = t.first; k <= t.last; ++k) {
-    const int sx = max(0, min(x + k, width - 1));
-    const float g = expf(-(k * k) / t.sig_square);
-    const float4 s = source[row + sx];
-    accum += g;
-    d.x += s.x * g;
-    d.y += s.y * g;
-    d.z += s.z * g;
-    d.w += s.w * g;
-  }
-  scratch[i] = make_float4(d.x / accum, d.y / accum, d.z / accum, d.w / accum);
 }
 
 // rows [row_begin,row_end): dest = vertical blur of scratch, rows clamped to [0,height-1]
 __global__ void k_blur_vertical(const float4* __restrict__ scratch, float4* __restrict__ dest,
                                 const float* __restrict__ sigma, int width, int height, int row_begin, int row_end,
                                 const float* max_sigma) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= (size_t)width * (row_end - row_begin)) return;
   if (all_sigma_zero(max_sigma)) return;
-  const size_t i = j + (size_t)row_begin * width;
-  const int x = (int)(i % width);
-  const int y = (int)(i / width);
-  const Taps t = taps_for(sigma[i]);
-  float accum = 0.0f;
-  float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  for (int k = t.first; k <= t.last; ++k) {
-    const int sy = max(0, min(y + k, height - 1));
-    const float g = expf(-(k * k) / t.sig_square);
-    const float4 s = scratch[(size_t)sy * width + x];
-    accum += g;
-    d.x += s.x * g;
-    d.y += s.y * g;
-    d.z += s.z * g;
-    d.w += s.w * g;
+  const size_t count = (size_t)width * (row_end - row_begin), first = (size_t)row_begin * width;
+  const size_t stride = (size_t)blockDim.x * gridDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+    const size_t i = first + j;
+    const int x = (int)(i % width);
+    const int y = (int)(i / width);
+    const Taps t = taps_for(sigma[i]);
+    float accum = 0.0f;
+    float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int k = t.first; k <= t.last; ++k) {
+      const int sy = max(0, min(y + k, height - 1));
+      const float g = expf(-(k * k) / t.sig_square);
+      const float4 s = scratch[(size_t)sy * width + x];
+      accum += g;
+      d.x += s.x * g;
+      d.y += s.y * g;
+      d.z += s.z * g;
+      d.w += s.w * g;
+    }
+    dest[i] = make_float4(d.x / accum, d.y / accum, d.z / accum, d.w / accum);
   }
-  dest[i] = make_float4(d.x / accum, d.y / accum, d.z / accum, d.w / accum);
+}
+
+inline unsigned grid_for(size_t n) {
+  const size_t blocks = (n + kThreads - 1) / kThreads;
+  return (unsigned)(blocks < kMaxBlocks ? blocks : kMaxBlocks);
 }
 
 }  // namespace
@@ -112,11 +124,9 @@ int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* s
   const int h_end = halo_rows < 0 ? height : (row_end + halo_rows < height ? row_end + halo_rows : height);
   const size_t n_all = (size_t)width * (h_end - h_begin);
   const size_t n_band = (size_t)width * (row_end - row_begin);
-  k_blur_horizontal<<<(unsigned)((n_all + kThreads - 1) / kThreads), kThreads, 0, stream>>>(src, scratch, dest, sigma, width,
-                                                                                            h_begin, h_end, max_sigma);
+  k_blur_horizontal<<<grid_for(n_all), kThreads, 0, stream>>>(src, scratch, dest, sigma, width, h_begin, h_end, max_sigma);
   RDC_CUDA(cudaGetLastError());
-  k_blur_vertical<<<(unsigned)((n_band + kThreads - 1) / kThreads), kThreads, 0, stream>>>(scratch, dest, sigma, width, height,
-                                                                                           row_begin, row_end, max_sigma);
+  k_blur_vertical<<<grid_for(n_band), kThreads, 0, stream>>>(scratch, dest, sigma, width, height, row_begin, row_end, max_sigma);
   RDC_CUDA(cudaGetLastError());
   return 0;
 }
