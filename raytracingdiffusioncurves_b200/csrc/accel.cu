@@ -237,6 +237,11 @@ __global__ void k_fit_boxes(const float4* leaf_box, int n, float pad, const int*
   }
 }
 
+__global__ void k_pad_boxes(const float4* leaf_box, uint32_t n, float pad, float4* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = padded(leaf_box[i], pad);
+}
+
 __global__ void k_single_leaf_root(const float4* leaf_box, float pad, BvhNode* nodes) {
   const float inf = __int_as_float(0x7f800000);
   nodes[0].lbox = padded(leaf_box[0], pad);
@@ -526,6 +531,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   TEMP_CUDA(cudaMalloc(&leaf_parent, n_runs * sizeof(int)));
   RunRecord* runs = up.alloc<RunRecord>(n_runs);
   uint4* run_ids = up.alloc<uint4>(n_runs);
+  float4* run_box = up.alloc<float4>(n_runs);
   BvhNode* nodes = up.alloc<BvhNode>(n_nodes);
   if (up.status) {
     free_temps();
@@ -542,6 +548,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   k_gather_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(order, runs_in, ids_in, box_in, n_runs, runs, run_ids, leaf_box);
   TEMP_CUDA(cudaGetLastError());
 
+  k_pad_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, n_runs, pad, run_box);
+  TEMP_CUDA(cudaGetLastError());
   TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
   if (n_runs == 1) {
     k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_box, pad, nodes);
@@ -570,6 +578,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   d.seg_chord_count = counts;
   d.runs = runs;
   d.run_ids = run_ids;
+  d.run_box = run_box;
   d.nodes = nodes;
   d.n_chords = n_chords;
   d.n_runs = n_runs;

@@ -67,6 +67,7 @@ struct DevScene {
   // acceleration structure: what rays touch
   const RunRecord* runs;           // [n_runs] Morton order
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K
+  const float4* run_box;           // [n_runs] Morton order: padded box of each run (per-tile run table)
   const BvhNode* nodes;            // [max(n_runs-1,1)]
   float4 root_box;                 // padded box of the whole scene (per-pixel angular culling)
   uint32_t n_segments, n_curves, n_chords, n_runs, n_nodes;
@@ -83,7 +84,7 @@ struct rdc_scene {
   uint32_t base_dirs_capacity = 0;
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
   unsigned int* work_counters = nullptr;  // k_render's tile counter pair (one render in flight per handle)
-  uint32_t grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // SM-filling grid size per kernel variant
+  uint32_t grid_blocks[16] = {};  // SM-filling grid size per kernel variant
   // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
   float4* part_rgbw = nullptr;
   float* part_blur = nullptr;

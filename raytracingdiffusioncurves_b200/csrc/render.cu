@@ -25,7 +25,8 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a tile: 8x4 pixels, one lane per pixel, all lanes on the same ray index
-constexpr int kMaxSplit = 4;                    // a tile's rays may be dealt to up to 4 work units (rdc_scene::split)
+constexpr int kMaxSplit = 4;
+constexpr uint32_t kTableRuns = 64;             // scenes with at most this many runs use the per-tile run table                    // a tile's rays may be dealt to up to 4 work units (rdc_scene::split)
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
@@ -66,7 +67,8 @@ struct Hit {
 
 struct Accel {
   const BvhNode* nodes;
-  const float4* runs;  // kRunVec float4 per run
+  const float4* runs;     // kRunVec float4 per run
+  const float4* run_box;  // padded box per run
   uint32_t n_runs;
 };
 
@@ -134,6 +136,31 @@ template <bool SMEM, bool PORTALS>
 __device__ __noinline__ void brute_force(const Accel& ac, float ox, float oy, float dx, float dy, float inv_dd,
                                          uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
   for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+}
+
+// Closest chord among the runs named by two bit masks (runs 0..31 and 32..63): the per-tile run table's
+// replacement for the tree on small scenes. Primary rays only.
+template <bool PORTALS, bool STATS>
+__device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint32_t m1, float ox, float oy, float dx, float dy,
+                                             Counters& cnt) {
+  Hit h;
+  if (STATS) cnt.rays++;
+  h.t = __int_as_float(0x7f800000);
+  h.s = 0.0f;
+  h.leaf = -1;
+  h.j = 0;
+  h.id = kMiss;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    uint32_t m = half ? m1 : m0;
+    while (m) {
+      const int r = __ffs(m) - 1 + 32 * half;
+      m &= m - 1;
+      if (STATS) cnt.chords += RDC_RUN;
+      test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+    }
+  }
+  return h;
 }
 
 // Closest chord along the ray. Ordered depth-first traversal: the nearer child first, the farther one on
@@ -234,9 +261,9 @@ struct Sample {
 // Carried state: F = product of portal filters, Bp = product of portal blurs, S = sum of 1/w_portal;
 // terminal hit: rgb = F*rgb_T, blur = Bp*blur_T, w = 1/(1/w_T + S) — the closed form of the reference's
 // recursion w = 1/(1/w' + 1/w_here) (:310).
-template <bool SMEM, bool PORTALS, bool STATS>
+template <bool SMEM, bool PORTALS, bool STATS, bool TABLE>
 __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac, float ox, float oy, float dx, float dy,
-                                            uint32_t& first_hit, Counters& cnt) {
+                                            uint32_t m0, uint32_t m1, uint32_t& first_hit, Counters& cnt) {
   const DevScene& sc = a.sc;
   Sample out{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   float Fr = 1.0f, Fg = 1.0f, Fb = 1.0f, Bp = 1.0f, S = 0.0f;
@@ -244,7 +271,9 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
   uint32_t skip_lo = 1, skip_hi = 0;  // empty range
   first_hit = kMiss;
   for (;;) {
-    Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi, cnt);
+    Hit h;
+    if (TABLE && depth == 0) h = table_closest<PORTALS, STATS>(ac, m0, m1, ox, oy, dx, dy, cnt);
+    else h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi, cnt);
     if (depth == 0) first_hit = h.id;
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
     if (STATS) cnt.shaded++;
@@ -355,23 +384,19 @@ __device__ __forceinline__ float atan2_bound(float y, float x) {
   return y < 0.0f ? -r : r;
 }
 
-// Which rays of this pixel can reach the scene at all? Ray i leaves a point of the pixel's jitter square
-// [bx,bx+zoom]x[by,by+zoom] in a direction whose angle lies in stratum (i, i+1]*2pi/N (base direction i
-// plus a jitter of at most one stratum). Seen from any point of the square, the scene's padded box lies
-// inside the angular interval [lo,hi] computed here from the box enlarged by the square (Minkowski sum).
-// Returns false when no culling applies (origin inside the box, fractional N, interval covers everything);
-// otherwise ray i can only hit if ((i - first) mod N) <= span.
-__device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float by, int& first, int& span) {
-  const int n = a.n_iter;
-  if (!a.cull || (float)n != a.n_rays || n < 8) return false;
-  const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
-  // rounding of the subtractions below and of the origin itself: a few ulp of the magnitudes involved
-  const float mag = fabsf(bx) + fabsf(by) + jit + fabsf(a.sc.root_box.x) + fabsf(a.sc.root_box.y) + fabsf(a.sc.root_box.z) +
-                    fabsf(a.sc.root_box.w);
+// Angular interval, in ray indices, under which `box` can be seen from ANY origin inside the rectangle
+// [ox0,ox1]x[oy0,oy1]. Ray i leaves its origin in a direction whose angle lies in stratum (i, i+1]*2pi/N (base
+// direction i plus a jitter of at most one stratum), so ray i can only hit the box if ((i - first) mod n) <= span.
+// Returns false when nothing can be excluded (an origin may lie inside the box, or the interval covers all rays).
+__device__ __forceinline__ bool angular_interval(float4 box, float ox0, float ox1, float oy0, float oy1, int n, int& first,
+                                                 int& span) {
+  // rounding of the subtractions below and of the origins themselves: a few ulp of the magnitudes involved
+  const float mag = fabsf(ox0) + fabsf(ox1) + fabsf(oy0) + fabsf(oy1) + fabsf(box.x) + fabsf(box.y) + fabsf(box.z) + fabsf(box.w);
   const float m = 4e-6f * mag + 1e-6f;
-  const float x0 = a.sc.root_box.x - (bx + jit) - m, x1 = a.sc.root_box.z - (bx - jit) + m;
-  const float y0 = a.sc.root_box.y - (by + jit) - m, y1 = a.sc.root_box.w - (by - jit) + m;
-  if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return false;  // the pixel may lie inside the box
+  // the box relative to every possible origin (Minkowski difference)
+  const float x0 = box.x - ox1 - m, x1 = box.z - ox0 + m;
+  const float y0 = box.y - oy1 - m, y1 = box.w - oy0 + m;
+  if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return false;
   const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
   float dmin = 0.0f, dmax = 0.0f;
 #pragma unroll
@@ -396,11 +421,19 @@ __device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float 
   return true;
 }
 
+// Which rays of this pixel can reach the scene at all? (origins: the pixel's jitter square)
+__device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float by, int& first, int& span) {
+  const int n = a.n_iter;
+  if (!a.cull || (float)n != a.n_rays || n < 8) return false;
+  const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
+  return angular_interval(a.sc.root_box, bx - jit, bx + jit, by - jit, by + jit, n, first, span);
+}
+
 #ifndef RDC_MIN_BLOCKS
 #define RDC_MIN_BLOCKS 4  // resident blocks per SM the register allocation aims for
 #endif
 
-template <bool SMEM, bool PORTALS, bool STATS>
+template <bool SMEM, bool PORTALS, bool STATS, bool TABLE>
 __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderArgs a) {
   extern __shared__ uint4 smem[];
   Accel ac;
@@ -415,12 +448,20 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     for (uint32_t i = threadIdx.x; i < node_words; i += kBlock) smem[i] = __ldg(gn + i);
 #pragma unroll 1
     for (uint32_t i = threadIdx.x; i < run_words; i += kBlock) smem[node_words + i] = __ldg(gr + i);
-    __syncthreads();
     ac.nodes = reinterpret_cast<const BvhNode*>(smem);
     ac.runs = reinterpret_cast<const float4*>(smem + node_words);
+    ac.run_box = a.sc.run_box;
+    if (TABLE) {
+      const uint4* gb = reinterpret_cast<const uint4*>(a.sc.run_box);
+#pragma unroll 1
+      for (uint32_t i = threadIdx.x; i < a.sc.n_runs; i += kBlock) smem[node_words + run_words + i] = __ldg(gb + i);
+      ac.run_box = reinterpret_cast<const float4*>(smem + node_words + run_words);
+    }
+    __syncthreads();
   } else {
     ac.nodes = a.sc.nodes;
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
+    ac.run_box = a.sc.run_box;
   }
 
   // Persistent warps: every warp of the (SM-filling) grid keeps fetching work units from one global
@@ -451,12 +492,74 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     const bool valid = ix < a.width && iy < a.row_end;
     const size_t local_pixel = (size_t)ly * a.width + ix;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
-    if (valid) {
-      // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
-      const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
-      const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
-                                   : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
-      const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
+    // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
+    const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
+    const float base_y = a.orzan ? (float)(int)((a.height - iy) - (a.height / 2)) * a.zoom + a.off_y
+                                 : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
+    const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
+
+    // one primary ray: generate, trace, shade, accumulate
+    auto do_ray = [&](int i, uint32_t m0, uint32_t m1) {
+      const float2 base = __ldg(a.base_dirs + i);
+      // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
+      const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
+      float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
+      if (a.use_aa) {
+        float js, jc;
+        const float ang = a.two_over_n * rdc_u01(rnd.x);
+        if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
+        else sincospi_general(ang, &js, &jc);
+        dx = base.x * jc - base.y * js;
+        dy = base.x * js + base.y * jc;
+        ox = base_x + rdc_u01(rnd.y) * a.zoom;
+        oy = base_y + rdc_u01(rnd.z) * a.zoom;
+      }
+      uint32_t first_hit;
+      Sample s = trace_ray<SMEM, PORTALS, STATS, TABLE>(a, ac, ox, oy, dx, dy, m0, m1, first_hit, cnt);
+      if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
+      weight_total += s.w;
+      cr += s.r * s.w;
+      cg += s.g * s.w;
+      cb += s.b * s.w;
+      blur += s.blur * s.w;
+    };
+
+    if (TABLE) {
+      // Per-tile run table (scenes of at most 64 runs): lane L works out, once per unit, under which ray
+      // indices runs L and L+32 can be seen from anywhere in the tile (all 32 pixels, jitter included).
+      // A ballot then tells every lane which runs ray i has to be tested against — usually one or two, and
+      // none at all for most rays of a sparse scene, which are then never generated. No tree walk.
+      const uint32_t tx0 = (tile % tiles_x) * kWarpTileW, ly0 = (tile / tiles_x) * kWarpTileH;
+      const uint32_t gy0 = a.row_begin + ((ly0 / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly0 % kStripRows;
+      const float xa = (float)(int)(tx0 - (a.width / 2)) * a.zoom + a.off_x;
+      const float xb = (float)(int)(tx0 + (kWarpTileW - 1) - (a.width / 2)) * a.zoom + a.off_x;
+      const float ya = a.orzan ? (float)(int)((a.height - gy0) - (a.height / 2)) * a.zoom + a.off_y
+                               : (float)(int)(gy0 - (a.height / 2)) * a.zoom + a.off_y;
+      const float yb = a.orzan ? (float)(int)((a.height - (gy0 + kWarpTileH - 1)) - (a.height / 2)) * a.zoom + a.off_y
+                               : (float)(int)((gy0 + kWarpTileH - 1) - (a.height / 2)) * a.zoom + a.off_y;
+      const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
+      const float ox0 = fminf(xa, xb) - jit, ox1 = fmaxf(xa, xb) + jit, oy0 = fminf(ya, yb) - jit, oy1 = fmaxf(ya, yb) + jit;
+      int first0 = 0, span0 = -1, first1 = 0, span1 = -1;  // span -1: never, n-1: always
+      if (lane < ac.n_runs && !angular_interval(ac.run_box[lane], ox0, ox1, oy0, oy1, a.n_iter, first0, span0)) {
+        first0 = 0; span0 = a.n_iter - 1;
+      }
+      if (lane + 32 < ac.n_runs && !angular_interval(ac.run_box[lane + 32], ox0, ox1, oy0, oy1, a.n_iter, first1, span1)) {
+        first1 = 0; span1 = a.n_iter - 1;
+      }
+#pragma unroll 1
+      for (int i = (int)q; i < a.n_iter; i += (int)a.split) {
+        int r0 = i - first0, r1 = i - first1;
+        if (r0 < 0) r0 += a.n_iter;
+        if (r1 < 0) r1 += a.n_iter;
+        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, r0 <= span0);
+        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, r1 <= span1);
+        if ((m0 | m1) == 0u) {  // no run can be reached: a miss for every pixel of the tile, adds nothing
+          if (a.hit_ids && valid) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
+          continue;
+        }
+        if (valid) do_ray(i, m0, m1);
+      }
+    } else if (valid) {
       // Ray indices that can reach the scene: [lo0,hi0] and (when the angular range wraps) [lo1,hi1],
       // visited in ascending order like the reference's loop. Everything else is a miss and adds nothing.
       int lo0 = 0, hi0 = a.n_iter - 1, lo1 = 1, hi1 = 0;
@@ -482,30 +585,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         const int lo = part ? lo1 : lo0, hi = part ? hi1 : hi0;
         // first index >= lo that belongs to this unit
         int i = lo + (int)((q + a.split - (uint32_t)lo % a.split) % a.split);
-        for (; i <= hi; i += (int)a.split) {
-          const float2 base = __ldg(a.base_dirs + i);
-          // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
-          const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
-          float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
-          if (a.use_aa) {
-            float js, jc;
-            const float ang = a.two_over_n * rdc_u01(rnd.x);
-            if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
-            else sincospi_general(ang, &js, &jc);
-            dx = base.x * jc - base.y * js;
-            dy = base.x * js + base.y * jc;
-            ox = base_x + rdc_u01(rnd.y) * a.zoom;
-            oy = base_y + rdc_u01(rnd.z) * a.zoom;
-          }
-          uint32_t first_hit;
-          Sample s = trace_ray<SMEM, PORTALS, STATS>(a, ac, ox, oy, dx, dy, first_hit, cnt);
-          if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
-          weight_total += s.w;
-          cr += s.r * s.w;
-          cg += s.g * s.w;
-          cb += s.b * s.w;
-          blur += s.blur * s.w;
-        }
+        for (; i <= hi; i += (int)a.split) do_ray(i, 0u, 0u);
       }
     }
     bool finish = true;
@@ -646,17 +726,23 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;
-  const size_t dyn = smem ? scene_bytes : 0;
-  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build
-  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0);
+  // Per-tile run table instead of the tree for primary rays: small scenes, whole number of rays >= 8, LBVH mode.
+  const bool table = smem && s->dev.n_runs <= kTableRuns && (float)n_iter == p.number_of_rays_per_pixel && n_iter >= 8 &&
+                     !a.brute && getenv("RDC_B200_NO_TABLE") == nullptr;
+  const size_t dyn = smem ? scene_bytes + (table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0;
+  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 run table
+  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (table ? 8 : 0);
   void (*kernel)(RenderArgs) = nullptr;
   switch (variant) {
-    case 0: kernel = k_render<false, false, false>; break;
-    case 1: kernel = k_render<true, false, false>; break;
-    case 2: kernel = k_render<false, true, false>; break;
-    case 3: kernel = k_render<true, true, false>; break;
-    case 6: kernel = k_render<false, true, true>; break;
-    default: kernel = k_render<true, true, true>; break;
+    case 0: kernel = k_render<false, false, false, false>; break;
+    case 1: kernel = k_render<true, false, false, false>; break;
+    case 2: kernel = k_render<false, true, false, false>; break;
+    case 3: kernel = k_render<true, true, false, false>; break;
+    case 6: kernel = k_render<false, true, true, false>; break;
+    case 7: kernel = k_render<true, true, true, false>; break;
+    case 9: kernel = k_render<true, false, false, true>; break;
+    case 11: kernel = k_render<true, true, false, true>; break;
+    default: kernel = k_render<true, true, true, true>; break;  // 15
   }
   if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
     int per_sm = 0, sms = 0;
