@@ -101,18 +101,17 @@ __device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, fl
   const float4* rp = ac.runs + (size_t)leaf * kRunVec;
   const float4 head = load16<SMEM>(rp);
   const int count = (int)__float_as_uint(head.y);
-  bool prev = rdc_edge(dx, dy, head.z - ox, head.w - oy) > 0.0f;
-  uint32_t crossed = 0;
+  // bit k of `above`: point k lies on the positive side of the ray's supporting line
+  uint32_t above = rdc_edge(dx, dy, head.z - ox, head.w - oy) > 0.0f ? 1u : 0u;
 #pragma unroll
   for (int v = 1; v < kRunVec; ++v) {
     if (2 * v - 2 >= count) break;
     const float4 q = load16<SMEM>(rp + v);
-    const bool s0 = rdc_edge(dx, dy, q.x - ox, q.y - oy) > 0.0f;
-    const bool s1 = rdc_edge(dx, dy, q.z - ox, q.w - oy) > 0.0f;
-    if (s0 != prev) crossed |= 1u << (2 * v - 2);
-    if (s1 != s0 && 2 * v - 1 < count) crossed |= 1u << (2 * v - 1);
-    prev = s1;
+    if (rdc_edge(dx, dy, q.x - ox, q.y - oy) > 0.0f) above |= 1u << (2 * v - 1);
+    if (rdc_edge(dx, dy, q.z - ox, q.w - oy) > 0.0f) above |= 1u << (2 * v);
   }
+  // chord j joins points j and j+1: crossed where their sides differ
+  uint32_t crossed = (above ^ (above >> 1)) & ((1u << count) - 1u);
   if (crossed == 0) return;
   const uint32_t first_id = __float_as_uint(head.x);
   const float2* pts = reinterpret_cast<const float2*>(rp) + 1;  // P0 follows the two header words
@@ -421,6 +420,33 @@ __device__ __forceinline__ bool angular_interval(float4 box, float ox0, float ox
   return true;
 }
 
+// bits [jlo, jhi] of a 32-bit word (empty when the range is)
+__device__ __forceinline__ uint32_t bit_range(int jlo, int jhi) {
+  jlo = max(jlo, 0);
+  jhi = min(jhi, 31);
+  if (jlo > jhi) return 0u;
+  const int len = jhi - jlo + 1;
+  return (len == 32 ? 0xFFFFFFFFu : (1u << len) - 1u) << jlo;
+}
+
+// For a run visible under ray indices {i : ((i - first) mod n) <= span}: which iterations j in [0, here) of
+// the chunk starting at iteration cb (ray i = q + ((cb + j) << shift)) are among them.
+__device__ __forceinline__ uint32_t iteration_mask(int first, int span, int q, int shift, int cb, int here, int n) {
+  if (span < 0) return 0u;
+  const uint32_t all = here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u;
+  if (span >= n - 1) return all;
+  const int step = 1 << shift;
+  auto rays = [&](int lo, int hi) {  // ray indices [lo, hi] -> iteration bits
+    if (hi < q) return 0u;
+    const int jlo = ((max(lo - q, 0) + step - 1) >> shift) - cb, jhi = ((hi - q) >> shift) - cb;
+    return bit_range(jlo, jhi);
+  };
+  const int last = first + span;
+  uint32_t m = rays(first, min(last, n - 1));
+  if (last >= n) m |= rays(0, last - n);
+  return m & all;
+}
+
 // Which rays of this pixel can reach the scene at all? (origins: the pixel's jitter square)
 __device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float by, int& first, int& span) {
   const int n = a.n_iter;
@@ -546,18 +572,32 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       if (lane + 32 < ac.n_runs && !angular_interval(ac.run_box[lane + 32], ox0, ox1, oy0, oy1, a.n_iter, first1, span1)) {
         first1 = 0; span1 = a.n_iter - 1;
       }
+      // Which of this unit's rays (i = q + j*split) fall into the interval of run L / L+32: one bit per
+      // iteration j, 32 iterations at a time. The OR over all lanes lists the iterations that have any
+      // candidate run; only those are visited.
+      const int n = a.n_iter, split = (int)a.split, shift = 31 - __clz(split);
+      const int n_it = (int)q < n ? (n - 1 - (int)q) / split + 1 : 0;
 #pragma unroll 1
-      for (int i = (int)q; i < a.n_iter; i += (int)a.split) {
-        int r0 = i - first0, r1 = i - first1;
-        if (r0 < 0) r0 += a.n_iter;
-        if (r1 < 0) r1 += a.n_iter;
-        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, r0 <= span0);
-        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, r1 <= span1);
-        if ((m0 | m1) == 0u) {  // no run can be reached: a miss for every pixel of the tile, adds nothing
-          if (a.hit_ids && valid) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = kMiss;
-          continue;
+      for (int cb = 0; cb < n_it; cb += 32) {
+        const int here = min(32, n_it - cb);
+        const uint32_t it0 = iteration_mask(first0, span0, (int)q, shift, cb, here, n);
+        const uint32_t it1 = iteration_mask(first1, span1, (int)q, shift, cb, here, n);
+        uint32_t any = __reduce_or_sync(0xFFFFFFFFu, it0 | it1);
+        if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
+          uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
+          while (none) {
+            const int j = __ffs(none) - 1;
+            none &= none - 1;
+            a.hit_ids[local_pixel * (size_t)n + (q + ((cb + j) << shift))] = kMiss;
+          }
         }
-        if (valid) do_ray(i, m0, m1);
+        while (any) {
+          const int j = __ffs(any) - 1;
+          any &= any - 1;
+          const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (it0 >> j) & 1u);
+          const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (it1 >> j) & 1u);
+          if (valid) do_ray((int)q + ((cb + j) << shift), m0, m1);
+        }
       }
     } else if (valid) {
       // Ray indices that can reach the scene: [lo0,hi0] and (when the angular range wraps) [lo1,hi1],
