@@ -458,6 +458,41 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     return fail(RDC_E_LIMIT);
   }
 
+  // Per-chord walk hints: where each stop walk stands once it has consumed every stop below the chord's
+  // smallest curve parameter (rdc_walk_hint). Hits on the chord start their walks there — usually zero
+  // steps — instead of at the segment's hint. Exact by the same argument as the per-segment hints.
+  {
+    std::vector<uint32_t> h_base(nseg + 1);
+    BUILD_CUDA(cudaMemcpyAsync(h_base.data(), base, (nseg + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    BUILD_CUDA(cudaStreamSynchronize(stream));
+    std::vector<uint4> hints(2 * (size_t)n_chords);
+    for (uint32_t sg = 0; sg < nseg; ++sg) {
+      const uint32_t c = a.curve_map[sg];
+      const int K = (int)(h_base[sg + 1] - h_base[sg]);
+      uint32_t prev[6] = {a.color_left_index[2 * c], a.color_right_index[2 * c], a.blur_index[2 * c], a.weight_index[2 * c],
+                          a.weight_degree_index[2 * c], a.color_right_index[2 * c]};
+      const uint32_t* idx[6] = {a.color_left_index, a.color_right_index, a.blur_index, a.weight_index, a.weight_degree_index,
+                                a.color_right_index};
+      const float* us[6] = {a.color_left_u, a.color_right_u, a.blur_u, a.weight_u, a.weight_degree_u, a.color_left_u};
+      for (int k = 0; k < K; ++k) {
+        const float cu_min = rdc_hit_u(k, K, 0.0f) + a.curve_index[sg];
+        uint32_t f[6];
+        for (int fam = 0; fam < 6; ++fam) {
+          // continue from the previous chord's position: the walk is monotone in the parameter
+          const uint32_t start = idx[fam][2 * c], end = start + idx[fam][2 * c + 1];
+          uint32_t j = prev[fam];
+          while (j < end && us[fam][j + 1] < cu_min) j++;
+          prev[fam] = f[fam] = j;
+        }
+        hints[2 * (size_t)(h_base[sg] + k)] = make_uint4(f[0], f[1], f[2], f[3]);
+        hints[2 * (size_t)(h_base[sg] + k) + 1] = make_uint4(f[4], f[5], 0u, 0u);
+      }
+    }
+    d.chord_walk = up.upload(hints.data(), hints.size());
+    BUILD_CUDA(cudaStreamSynchronize(stream));  // `hints` leaves scope
+    if (up.status) return fail(up.status);
+  }
+
   // chords stay in original order (hit ids, download hook); runs + tree are what rays touch
   float4* chord_geom = up.alloc<float4>(n_chords);
   uint4* chord_ids = up.alloc<uint4>(n_chords);

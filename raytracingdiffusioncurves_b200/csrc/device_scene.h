@@ -64,6 +64,7 @@ struct DevScene {
   const uint32_t* seg_chord_base;  // [n_segments+1] id of chord 0 of each segment
   const uint32_t* seg_chord_count; // [n_segments]   K
   const SegWalk* seg_walk;         // [n_segments]
+  const uint4* chord_walk;         // [2*n_chords] per chord: walk start of left, right, blur, weight | degree, portal-left
   // acceleration structure: what rays touch
   const RunRecord* runs;           // [n_runs] Morton order
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K

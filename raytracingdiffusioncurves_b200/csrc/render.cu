@@ -282,11 +282,13 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
     // walk ranges of this segment (SegWalk): the stop walks start where the segment starts
     const uint4* wp = reinterpret_cast<const uint4*>(sc.seg_walk + seg);
     const uint4 wc = __ldg(wp), ws = __ldg(wp + 1), wd = __ldg(wp + 2);
+    // ... and, finer, where this chord starts (chord_walk): the walks then rarely take a step
+    const uint4 cw = __ldg(sc.chord_walk + 2 * (size_t)h.id), cw2 = __ldg(sc.chord_walk + 2 * (size_t)h.id + 1);
     const uint32_t curve = wd.z, ordinal = wd.w;
     const float cu = u + ordinal;
-    const float blur_here = scalar_stop(sc.blur, ws.x, ws.y, cu);
-    const float wm = scalar_stop(sc.weight, ws.z, ws.w, cu);
-    const float e = scalar_stop(sc.weight_degree, wd.x, wd.y, cu);
+    const float blur_here = scalar_stop(sc.blur, cw.z, ws.y, cu);
+    const float wm = scalar_stop(sc.weight, cw.w, ws.w, cu);
+    const float e = scalar_stop(sc.weight_degree, cw2.x, wd.y, cu);
     const float w_here = wm * rdc_weight_falloff(h.t, e);
     rdc_f2 v[4];
     load_control_points(sc, seg, v);
@@ -311,10 +313,10 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
         float ndx = m.x * rc - m.y * rs;
         float ndy = m.y * rc + m.x * rs;
         float fr, fg, fb;
-        if (right) colour_stop(wc.z, wc.w, sc.color_right.u, sc.color_right.rgb, cu, fr, fg, fb);
+        if (right) colour_stop(cw.y, wc.w, sc.color_right.u, sc.color_right.rgb, cu, fr, fg, fb);
         else {  // right list's range on the left arrays (:297)
           const uint4 wq = __ldg(wp + 3);
-          colour_stop(wq.x, wq.y, sc.color_left.u, sc.color_left.rgb, cu, fr, fg, fb);
+          colour_stop(cw2.y, wq.y, sc.color_left.u, sc.color_left.rgb, cu, fr, fg, fb);
         }
         Fr *= fr; Fg *= fg; Fb *= fb;
         Bp *= blur_here;
@@ -330,8 +332,8 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
       }
     }
     float r, g, b;
-    if (right) colour_stop(wc.z, wc.w, sc.color_right.u, sc.color_right.rgb, cu, r, g, b);
-    else colour_stop(wc.x, wc.y, sc.color_left.u, sc.color_left.rgb, cu, r, g, b);
+    if (right) colour_stop(cw.y, wc.w, sc.color_right.u, sc.color_right.rgb, cu, r, g, b);
+    else colour_stop(cw.x, wc.y, sc.color_left.u, sc.color_left.rgb, cu, r, g, b);
     if (PORTALS && depth > 0) {
       out.r = Fr * r; out.g = Fg * g; out.b = Fb * b;
       out.blur = Bp * blur_here;
