@@ -159,6 +159,13 @@ int rdc_gaussian_blur_band(void* dest, const void* source, const float* sigma, v
  *      minus window system: render -> [blur] -> copy to host -> synchronise ---- */
 int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
                              rdc_stream stream);
+/* Pipelined form: only enqueues (render and blur on `stream`, the copy to `host_image` — pinned memory — on the
+ * handle's own copy stream, two device images used in turn), so the copy of one frame overlaps the rendering of the
+ * next. rdc_frame_wait blocks until every enqueued frame is in host memory. Give consecutive frames different
+ * host buffers. rdc_render_frame_to_host = async + wait. */
+int rdc_render_frame_to_host_async(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
+                                   rdc_stream stream);
+int rdc_frame_wait(rdc_scene* scene);
 
 /* ---- output conventions of the F11 screenshot (glfw_events.cpp:73-94) ---- */
 /* float4 image -> RGBA8: min(v*255,255), NaN -> 0, rows flipped when flip != 0. Host memory. */

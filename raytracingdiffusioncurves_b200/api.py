@@ -99,6 +99,8 @@ PROTOTYPES = {
     "rdc_gaussian_blur_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p]),
     "rdc_render_frame_to_host": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_void_p, C.c_void_p]),
+    "rdc_render_frame_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_void_p, C.c_void_p]),
+    "rdc_frame_wait": (C.c_int, [C.c_void_p]),
     "rdc_image_to_rgba8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rdc_write_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "rdc_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
@@ -313,6 +315,19 @@ class Scene:
     def render_frame_to_host(self, params: FrameParams, use_blur: bool, host_image_ptr: int, stream: int = 0) -> None:
         _check(_lib.rdc_render_frame_to_host(self._h, C.byref(params), int(use_blur), C.c_void_p(host_image_ptr),
                                              C.c_void_p(stream)), "rdc_render_frame_to_host")
+
+
+def _scene_async(self, params, use_blur, host_image_ptr, stream=0):
+    _check(_lib.rdc_render_frame_to_host_async(self._h, C.byref(params), int(use_blur), C.c_void_p(host_image_ptr), C.c_void_p(stream)),
+           "rdc_render_frame_to_host_async")
+
+
+def _scene_wait(self):
+    _check(_lib.rdc_frame_wait(self._h), "rdc_frame_wait")
+
+
+Scene.render_frame_to_host_async = _scene_async
+Scene.frame_wait = _scene_wait
 
 
 def gaussian_blur(dest_ptr: int, src_ptr: int, sigma_ptr: int, scratch_ptr: int, width: int, height: int,

@@ -309,7 +309,16 @@ void destroy_scene(rdc_scene* s) {
   cudaGetDevice(&prev);
   cudaSetDevice(s->device);
   for (void* p : s->allocations) cudaFree(p);
-  cudaFree(s->frame_image);
+  cudaFree(s->frame_image[0]);
+  cudaFree(s->frame_image[1]);
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamDestroy(s->copy_stream);
+    for (int k = 0; k < 2; ++k) {
+      cudaEventDestroy(s->rendered[k]);
+      cudaEventDestroy(s->copied[k]);
+    }
+  }
   cudaFree(s->frame_scratch);
   cudaFree(s->frame_sigma);
   cudaFree(s->part_rgbw);

@@ -243,8 +243,10 @@ void setupCurand(void* states, int width, int height, rdc_stream stream) {
   if (width <= 0 || height <= 0) rdc::set_error("setupCurand: bad size");
 }
 
-int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
-                             rdc_stream stream) {
+// Enqueue-only frame: render -> [blur] on `stream`, then the copy to host memory on the handle's own copy
+// stream, so that the copy of frame f overlaps the rendering of frame f+1 (two device images, used in turn).
+int rdc_render_frame_to_host_async(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
+                                   rdc_stream stream) {
   if (!scene || !params || !host_image) {
     rdc::set_error("render frame: null argument");
     return RDC_E_INVALID;
@@ -257,23 +259,36 @@ int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, i
     }
     const size_t rows = params->row_end - params->row_begin;
     const size_t n = rows * params->image_width;
+    if (!scene->copy_stream) {
+      RDC_CUDA(cudaStreamCreateWithFlags(&scene->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        RDC_CUDA(cudaEventCreateWithFlags(&scene->rendered[k], cudaEventDisableTiming));
+        RDC_CUDA(cudaEventCreateWithFlags(&scene->copied[k], cudaEventDisableTiming));
+      }
+    }
     if (n > scene->frame_pixels) {  // grow-only frame buffers owned by the handle
       RDC_CUDA(cudaStreamSynchronize(st));
-      cudaFree(scene->frame_image);
+      RDC_CUDA(cudaStreamSynchronize(scene->copy_stream));
+      cudaFree(scene->frame_image[0]);
+      cudaFree(scene->frame_image[1]);
       cudaFree(scene->frame_scratch);
       cudaFree(scene->frame_sigma);
-      scene->frame_image = scene->frame_scratch = nullptr;
+      scene->frame_image[0] = scene->frame_image[1] = scene->frame_scratch = nullptr;
       scene->frame_sigma = nullptr;
       scene->frame_pixels = 0;
-      RDC_CUDA(cudaMalloc((void**)&scene->frame_image, n * sizeof(float4)));
+      RDC_CUDA(cudaMalloc((void**)&scene->frame_image[0], n * sizeof(float4)));
+      RDC_CUDA(cudaMalloc((void**)&scene->frame_image[1], n * sizeof(float4)));
       RDC_CUDA(cudaMalloc((void**)&scene->frame_scratch, n * sizeof(float4)));
       RDC_CUDA(cudaMalloc((void**)&scene->frame_sigma, (n + 1) * sizeof(float)));
       scene->frame_pixels = n;
     }
-    float4* image = scene->frame_image;
+    const int slot = scene->frame_slot ^= 1;
+    float4* image = scene->frame_image[slot];
     float* sigma = scene->frame_sigma;
     float* flag = sigma + scene->frame_pixels;
     rdc_frame_params p = *params;
+    // the copy that last read this image must be over before it is rendered into again
+    RDC_CUDA(cudaStreamWaitEvent(st, scene->copied[slot], 0));
     if (use_blur) {
       RDC_CUDA(cudaMemsetAsync(flag, 0, sizeof(float), st));
       p.max_sigma = flag;
@@ -282,10 +297,29 @@ int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, i
     if (rc == 0 && use_blur)
       rc = rdc::gaussian_blur(image, image, sigma, scene->frame_scratch, (int)params->image_width, (int)rows, 0, (int)rows, flag, st);
     if (rc != 0) return rc;
-    RDC_CUDA(cudaMemcpyAsync(host_image, image, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
-    RDC_CUDA(cudaStreamSynchronize(st));
+    RDC_CUDA(cudaEventRecord(scene->rendered[slot], st));
+    RDC_CUDA(cudaStreamWaitEvent(scene->copy_stream, scene->rendered[slot], 0));
+    RDC_CUDA(cudaMemcpyAsync(host_image, image, n * sizeof(float4), cudaMemcpyDeviceToHost, scene->copy_stream));
+    RDC_CUDA(cudaEventRecord(scene->copied[slot], scene->copy_stream));
     return 0;
   });
+}
+
+// Blocks until every frame enqueued with rdc_render_frame_to_host_async has reached host memory.
+int rdc_frame_wait(rdc_scene* scene) {
+  if (!scene) {
+    rdc::set_error("frame wait: null argument");
+    return RDC_E_INVALID;
+  }
+  if (scene->copy_stream) RDC_CUDA(cudaStreamSynchronize(scene->copy_stream));
+  return 0;
+}
+
+int rdc_render_frame_to_host(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
+                             rdc_stream stream) {
+  int rc = rdc_render_frame_to_host_async(scene, params, use_blur, host_image, stream);
+  if (rc != 0) return rc;
+  return rdc_frame_wait(scene);
 }
 
 int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint8_t* out) {

@@ -92,8 +92,11 @@ struct rdc_scene {
   unsigned int* tile_arrivals = nullptr;
   size_t part_capacity = 0, tile_capacity = 0;
   // frame buffers of rdc_render_frame_to_host, grown on demand and kept (no per-frame allocation)
-  float4* frame_image = nullptr;
+  float4* frame_image[2] = {nullptr, nullptr};  // used in turn: the copy of one overlaps the rendering of the other
   float4* frame_scratch = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  int frame_slot = 0;
   float* frame_sigma = nullptr;  // pixels + 1: the extra float is the max-sigma flag
   size_t frame_pixels = 0;
 };

@@ -96,8 +96,8 @@ __device__ __forceinline__ float slab_rcp(float d) {
 // the chords whose end points lie on different sides of the ray; the (rare) marked ones are then resolved
 // in a rolled loop that re-reads their two points — same inputs, same operations, same bits.
 template <bool SMEM, bool PORTALS>
-__device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
-                                         uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
+__device__ __forceinline__ int test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
+                                        uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
   const float4* rp = ac.runs + (size_t)leaf * kRunVec;
   const float4 head = load16<SMEM>(rp);
   const int count = (int)__float_as_uint(head.y);
@@ -112,7 +112,7 @@ __device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, fl
   }
   // chord j joins points j and j+1: crossed where their sides differ
   uint32_t crossed = (above ^ (above >> 1)) & ((1u << count) - 1u);
-  if (crossed == 0) return;
+  if (crossed == 0) return count;
   const uint32_t first_id = __float_as_uint(head.x);
   const float2* pts = reinterpret_cast<const float2*>(rp) + 1;  // P0 follows the two header words
   while (crossed) {
@@ -128,6 +128,7 @@ __device__ __forceinline__ void test_run(const Accel& ac, int leaf, float ox, fl
       }
     }
   }
+  return count;  // chords looked at
 }
 
 // Every run against the ray: the kernel behind RDC_TRAVERSAL_BRUTE_FORCE (validation only, kept out of line).
@@ -155,8 +156,8 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint3
     while (m) {
       const int r = __ffs(m) - 1 + 32 * half;
       m &= m - 1;
-      if (STATS) cnt.chords += RDC_RUN;
-      test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+      const int looked = test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+      if (STATS) cnt.chords += looked;
     }
   }
   return h;
@@ -180,7 +181,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   const float inv_dd = PORTALS ? rdc_inv_dd(dx, dy, primary) : 1.0f;
   if (brute) {
     brute_force<SMEM, PORTALS>(ac, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
-    if (STATS) cnt.chords += ac.n_runs * RDC_RUN;
+    if (STATS) cnt.chords += ac.n_runs * RDC_RUN;  // upper bound
     return h;
   }
   const float idx = slab_rcp(dx), idy = slab_rcp(dy);
@@ -189,8 +190,8 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   int node = 0;
   for (;;) {
     if (node < 0) {
-      if (STATS) cnt.chords += RDC_RUN;
-      test_run<SMEM, PORTALS>(ac, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      const int looked = test_run<SMEM, PORTALS>(ac, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      if (STATS) cnt.chords += looked;
     } else {
       if (STATS) cnt.nodes++;
       const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);

@@ -239,6 +239,26 @@ def test_frame_to_host_equals_device_path(xml_dir, api):
     assert np.array_equal(bits(host.numpy()), bits(dev["blurred"]))
 
 
+def test_pipelined_frames_equal_frame_by_frame(xml_dir, api):
+    import torch
+
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))
+    w, h, n = 96, 64, 8
+    s = torch.cuda.current_stream().cuda_stream
+    want = []
+    for f in range(4):
+        buf = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+        r.scene.render_frame_to_host(api.default_frame_params(w, h, n, zoom_factor=512 / h, frame=f), True, buf.data_ptr(), s)
+        want.append(buf.numpy().copy())
+    bufs = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(4)]
+    for f in range(4):
+        r.scene.render_frame_to_host_async(api.default_frame_params(w, h, n, zoom_factor=512 / h, frame=f), True, bufs[f].data_ptr(), s)
+    r.scene.frame_wait()
+    for f in range(4):
+        assert np.array_equal(bits(bufs[f].numpy()), bits(want[f])), f
+    assert not np.array_equal(bits(want[0]), bits(want[1]))  # frames differ: the frame number keys the generator
+
+
 def test_bad_arguments_are_reported(xml_dir, api):
     r = GpuRenderer(os.path.join(xml_dir, "arch.xml"))
     import torch
