@@ -139,10 +139,13 @@ __device__ __noinline__ void brute_force(const Accel& ac, float ox, float oy, fl
 }
 
 // Closest chord among the runs named by two bit masks (runs 0..31 and 32..63): the per-tile run table's
-// replacement for the tree on small scenes. Primary rays only.
+// replacement for the tree on small scenes. Primary rays only. The run that the lane's previous ray hit
+// goes first — neighbouring strata mostly hit the same run — which gives a tight bound early; every other
+// candidate first has to pass the slab test of its padded box against that bound (the same conservative
+// test the tree applies to a leaf's box), and most do not.
 template <bool PORTALS, bool STATS>
-__device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint32_t m1, float ox, float oy, float dx, float dy,
-                                             Counters& cnt) {
+__device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint32_t m1, int& last_run, float ox, float oy, float dx,
+                                             float dy, Counters& cnt) {
   Hit h;
   if (STATS) cnt.rays++;
   h.t = __int_as_float(0x7f800000);
@@ -150,16 +153,35 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint3
   h.leaf = -1;
   h.j = 0;
   h.id = kMiss;
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    uint32_t m = half ? m1 : m0;
-    while (m) {
-      const int r = __ffs(m) - 1 + 32 * half;
-      m &= m - 1;
-      const int looked = test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+  if (last_run >= 0) {
+    const uint32_t bit = 1u << (last_run & 31);
+    uint32_t& m = last_run < 32 ? m0 : m1;
+    if (m & bit) {
+      m &= ~bit;
+      const int looked = test_run<true, PORTALS>(ac, last_run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
       if (STATS) cnt.chords += looked;
     }
   }
+  if ((m0 | m1) != 0u) {
+    const float idx = slab_rcp(dx), idy = slab_rcp(dy);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t m = half ? m1 : m0;
+      while (m) {
+        const int r = __ffs(m) - 1 + 32 * half;
+        m &= m - 1;
+        const float4 b = ac.run_box[r];
+        float te;
+        const float tn = rdc_slab(ox, oy, idx, idy, b.x, b.y, b.z, b.w, &te);
+        if (STATS) cnt.nodes++;
+        if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
+          const int looked = test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+          if (STATS) cnt.chords += looked;
+        }
+      }
+    }
+  }
+  if (h.leaf >= 0) last_run = h.leaf;
   return h;
 }
 
@@ -263,7 +285,7 @@ struct Sample {
 // recursion w = 1/(1/w' + 1/w_here) (:310).
 template <bool SMEM, bool PORTALS, bool STATS, bool TABLE>
 __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac, float ox, float oy, float dx, float dy,
-                                            uint32_t m0, uint32_t m1, uint32_t& first_hit, Counters& cnt) {
+                                            uint32_t m0, uint32_t m1, int& last_run, uint32_t& first_hit, Counters& cnt) {
   const DevScene& sc = a.sc;
   Sample out{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   float Fr = 1.0f, Fg = 1.0f, Fb = 1.0f, Bp = 1.0f, S = 0.0f;
@@ -272,7 +294,7 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
   first_hit = kMiss;
   for (;;) {
     Hit h;
-    if (TABLE && depth == 0) h = table_closest<PORTALS, STATS>(ac, m0, m1, ox, oy, dx, dy, cnt);
+    if (TABLE && depth == 0) h = table_closest<PORTALS, STATS>(ac, m0, m1, last_run, ox, oy, dx, dy, cnt);
     else h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi, cnt);
     if (depth == 0) first_hit = h.id;
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
@@ -527,6 +549,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
                                  : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
     const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
 
+    int last_run = -1;  // run table: the run this lane's previous ray hit
     // one primary ray: generate, trace, shade, accumulate
     auto do_ray = [&](int i, uint32_t m0, uint32_t m1) {
       const float2 base = __ldg(a.base_dirs + i);
@@ -544,7 +567,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         oy = base_y + rdc_u01(rnd.z) * a.zoom;
       }
       uint32_t first_hit;
-      Sample s = trace_ray<SMEM, PORTALS, STATS, TABLE>(a, ac, ox, oy, dx, dy, m0, m1, first_hit, cnt);
+      Sample s = trace_ray<SMEM, PORTALS, STATS, TABLE>(a, ac, ox, oy, dx, dy, m0, m1, last_run, first_hit, cnt);
       if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
       weight_total += s.w;
       cr += s.r * s.w;
