@@ -45,9 +45,9 @@ XML_DIR = os.path.join(ROOT, "tests", "golden", "xmls")
 F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
 
 # From the committed `ncu --set full` capture of k_render on the headline workload
-# (profiles/r01_k_render_v4_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
+# (profiles/r01_k_render_v7_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
 NCU_CAPTURE = {
-    "arch_1080p_128rpp": {"dram_bytes": 5.218048e6 + 163.349248e6, "issue_active": 0.8269, "source": "profiles/r01_k_render_v4_ncu_summary.txt"},
+    "arch_1080p_128rpp": {"dram_bytes": 3.554304e6 + 156.500736e6, "issue_active": 0.8174, "source": "profiles/r01_k_render_v7_ncu_summary.txt"},
 }
 
 
