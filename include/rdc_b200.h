@@ -61,6 +61,9 @@ int rdc_ingest_xml_file(const char* path, const rdc_ingest_options* opts, rdc_ho
 int rdc_ingest_xml_memory(const char* text, size_t len, const rdc_ingest_options* opts, rdc_host_scene** out);
 int rdc_host_scene_arrays(const rdc_host_scene* scene, rdc_scene_arrays* out);
 void rdc_host_scene_destroy(rdc_host_scene* scene);
+/* Binary cache of an ingested scene (skips XML parsing on the next run; same arrays bit for bit). */
+int rdc_host_scene_save(const rdc_host_scene* scene, const char* path);
+int rdc_host_scene_load(const char* path, rdc_host_scene** out);
 /* canonical text dump of the element tree the loader sees (parser tests) ; caller frees with rdc_free */
 int rdc_xml_dump_file(const char* path, char** out_text);
 void rdc_free(void* p);

@@ -82,6 +82,8 @@ PROTOTYPES = {
     "rdc_ingest_xml_memory": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(IngestOptions), C.POINTER(C.c_void_p)]),
     "rdc_host_scene_arrays": (C.c_int, [C.c_void_p, C.POINTER(SceneArrays)]),
     "rdc_host_scene_destroy": (None, [C.c_void_p]),
+    "rdc_host_scene_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "rdc_host_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "rdc_xml_dump_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "rdc_free": (None, [C.c_void_p]),
     "rdc_default_accel_options": (None, [C.POINTER(AccelOptions)]),
@@ -184,6 +186,15 @@ class HostScene:
         _check(_lib.rdc_ingest_xml_memory(text, len(text), C.byref(options) if options else None, C.byref(h)),
                "rdc_ingest_xml_memory")
         return cls(h.value)
+
+    @classmethod
+    def from_cache(cls, path: str) -> "HostScene":
+        h = C.c_void_p()
+        _check(_lib.rdc_host_scene_load(os.fsencode(path), C.byref(h)), "rdc_host_scene_load")
+        return cls(h.value)
+
+    def save(self, path: str) -> None:
+        _check(_lib.rdc_host_scene_save(self._h, os.fsencode(path)), "rdc_host_scene_save")
 
     def close(self) -> None:
         if self._h:

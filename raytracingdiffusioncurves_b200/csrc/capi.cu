@@ -6,6 +6,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "device_scene.h"
 #include "host_scene.h"
@@ -36,6 +37,28 @@ int guarded(int parse_code, F&& body) {
   }
 }
 
+}  // namespace
+
+// ---- binary scene cache: the ingested arrays, little-endian, versioned ----
+namespace {
+const char kCacheMagic[8] = {'R', 'D', 'C', 'S', 'C', 'N', '0', '1'};
+
+template <class T>
+bool put_vec(std::FILE* f, const std::vector<T>& v) {
+  const uint64_t n = v.size();
+  return std::fwrite(&n, sizeof n, 1, f) == 1 && (n == 0 || std::fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T>
+bool get_vec(std::FILE* f, std::vector<T>& v) {
+  uint64_t n = 0;
+  if (std::fread(&n, sizeof n, 1, f) != 1 || n > (1ull << 32)) return false;
+  v.resize(n);
+  return n == 0 || std::fread(v.data(), sizeof(T), n, f) == n;
+}
+template <class Op>
+bool stop_list_io(std::FILE* f, rdc_host_scene::StopList& l, Op&& io) {
+  return io(f, l.index) && io(f, l.value) && io(f, l.u);
+}
 }  // namespace
 
 extern "C" {
@@ -109,6 +132,70 @@ int rdc_host_scene_arrays(const rdc_host_scene* scene, rdc_scene_arrays* out) {
 }
 
 void rdc_host_scene_destroy(rdc_host_scene* scene) { delete scene; }
+
+int rdc_host_scene_save(const rdc_host_scene* scene, const char* path) {
+  if (!scene || !path) {
+    rdc::set_error("scene save: null argument");
+    return RDC_E_INVALID;
+  }
+  std::FILE* f = std::fopen(path, "wb");
+  if (!f) {
+    rdc::set_error("scene save: cannot open %s", path);
+    return RDC_E_IO;
+  }
+  rdc_host_scene& s = const_cast<rdc_host_scene&>(*scene);
+  const int32_t dims[2] = {s.image_width, s.image_height};
+  auto put = [](std::FILE* fp, auto& v) { return put_vec(fp, v); };
+  bool ok = std::fwrite(kCacheMagic, 1, 8, f) == 8 && std::fwrite(dims, sizeof dims, 1, f) == 1 &&
+            std::fwrite(s.n_true, sizeof s.n_true, 1, f) == 1 && put_vec(f, s.vertices) && put_vec(f, s.segment_indices) &&
+            put_vec(f, s.curve_map) && put_vec(f, s.curve_index) && put_vec(f, s.curve_map_inverse) && put_vec(f, s.curve_connect);
+  for (rdc_host_scene::StopList* l : {&s.color_left, &s.color_right, &s.blur, &s.weight, &s.weight_degree}) ok = ok && stop_list_io(f, *l, put);
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) {
+    rdc::set_error("scene save: write failed for %s", path);
+    return RDC_E_IO;
+  }
+  return 0;
+}
+
+int rdc_host_scene_load(const char* path, rdc_host_scene** out) {
+  if (!path || !out) {
+    rdc::set_error("scene load: null argument");
+    return RDC_E_INVALID;
+  }
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    rdc::set_error("scene load: cannot open %s", path);
+    return RDC_E_IO;
+  }
+  return guarded(RDC_E_PARSE, [&]() {
+    auto* s = new rdc_host_scene();
+    char magic[8];
+    int32_t dims[2];
+    auto get = [](std::FILE* fp, auto& v) { return get_vec(fp, v); };
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, kCacheMagic, 8) == 0 && std::fread(dims, sizeof dims, 1, f) == 1 &&
+              std::fread(s->n_true, sizeof s->n_true, 1, f) == 1 && get_vec(f, s->vertices) && get_vec(f, s->segment_indices) &&
+              get_vec(f, s->curve_map) && get_vec(f, s->curve_index) && get_vec(f, s->curve_map_inverse) && get_vec(f, s->curve_connect);
+    for (rdc_host_scene::StopList* l : {&s->color_left, &s->color_right, &s->blur, &s->weight, &s->weight_degree}) ok = ok && stop_list_io(f, *l, get);
+    std::fclose(f);
+    // structural checks: the arrays must describe a consistent scene
+    const size_t nseg = s->segment_indices.size(), ncurves = s->curve_connect.size();
+    ok = ok && nseg > 0 && ncurves > 0 && s->vertices.size() % 3 == 0 && s->curve_map.size() == nseg && s->curve_index.size() == nseg &&
+         s->curve_map_inverse.size() == ncurves;
+    for (rdc_host_scene::StopList* l : {&s->color_left, &s->color_right, &s->blur, &s->weight, &s->weight_degree})
+      ok = ok && l->index.size() == 2 * ncurves && l->value.size() == l->u.size() * (size_t)l->stride && l->u.size() >= 2;
+    if (!ok) {
+      delete s;
+      rdc::set_error("scene load: %s is not a scene cache of this version", path);
+      return RDC_E_PARSE;
+    }
+    s->image_width = dims[0];
+    s->image_height = dims[1];
+    s->sealed = true;
+    *out = s;
+    return 0;
+  });
+}
 
 int rdc_xml_dump_file(const char* path, char** out_text) {
   if (!path || !out_text) {

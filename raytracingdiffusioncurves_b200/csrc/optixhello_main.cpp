@@ -32,7 +32,7 @@
   } while (0)
 
 static void usage_options() {
-  std::cout << "options: --width W --height H --frames N --out file.ppm|file.png --zoom Z --offset-x X --offset-y Y\n"
+  std::cout << "options: --width W --height H --frames N --out file.ppm|file.png --save-cache scene.rdc --zoom Z --offset-x X --offset-y Y\n"
                "         --seed S --max-depth D --tolerance T --curve-width R --endcap-size E --weight-degree G\n"
                "         --native (not an Orzan save) --no-blur --no-aa --denoiser (ignored) --brute-force --device I\n";
 }
@@ -63,7 +63,7 @@ int main(int argc, char* argv[]) {
   int out_w = 0, out_h = 0;
   float zoom = -1.0f, off_x = RDC_DEFAULT_OFFSET_X, off_y = RDC_DEFAULT_OFFSET_Y;
   unsigned seed = 0;
-  std::string out_path;
+  std::string out_path, cache_path;
   for (int i = 3; i < argc; ++i) {
     std::string a = argv[i];
     auto value = [&]() -> const char* {
@@ -77,6 +77,7 @@ int main(int argc, char* argv[]) {
     else if (a == "--height") out_h = std::atoi(value());
     else if (a == "--frames") frames = std::atoi(value());
     else if (a == "--out") out_path = value();
+    else if (a == "--save-cache") cache_path = value();
     else if (a == "--zoom") zoom = (float)std::atof(value());
     else if (a == "--offset-x") off_x = (float)std::atof(value());
     else if (a == "--offset-y") off_y = (float)std::atof(value());
@@ -109,7 +110,11 @@ int main(int argc, char* argv[]) {
   cudaStream_t stream;
   CALL_CHECK((int)cudaStreamCreate(&stream));
   rdc_host_scene* host = nullptr;
-  CALL_CHECK(rdc_ingest_xml_file(file_name.c_str(), &ingest, &host));
+  // a ".rdc" path names a binary scene cache written by --save-cache (skips the XML parse)
+  const bool cached = file_name.size() > 4 && file_name.compare(file_name.size() - 4, 4, ".rdc") == 0;
+  if (cached) CALL_CHECK(rdc_host_scene_load(file_name.c_str(), &host));
+  else CALL_CHECK(rdc_ingest_xml_file(file_name.c_str(), &ingest, &host));
+  if (!cache_path.empty()) CALL_CHECK(rdc_host_scene_save(host, cache_path.c_str()));
   rdc_scene_arrays arrays;
   CALL_CHECK(rdc_host_scene_arrays(host, &arrays));
   rdc_scene* scene = nullptr;

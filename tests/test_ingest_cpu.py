@@ -124,3 +124,20 @@ def test_image_to_rgba8_follows_the_screenshot_convention():
     out = api.image_to_rgba8(img, flip=False)
     assert out[0, 0].tolist() == [127, 255, 0, 255] and out[1, 2].tolist() == [255, 63, 0, 255]
     assert np.array_equal(api.image_to_rgba8(img, flip=True), out[::-1])
+
+
+def test_scene_cache_round_trip(xml_dir, tmp_path):
+    for name in ("arch.xml", "PortalDemo.xml", "DiffusionCurvePack/dolphin.xml"):
+        a = api.HostScene.from_xml_file(os.path.join(xml_dir, name))
+        path = str(tmp_path / "scene.rdc")
+        a.save(path)
+        b = api.HostScene.from_cache(path)
+        assert_scene_equal(a.to_numpy(), b.to_numpy())
+    bad = tmp_path / "bad.rdc"
+    bad.write_bytes(b"not a cache at all")
+    with pytest.raises(api.RdcError) as e:
+        api.HostScene.from_cache(str(bad))
+    assert e.value.code == -2
+    with pytest.raises(api.RdcError) as e:
+        api.HostScene.from_cache(str(tmp_path / "missing.rdc"))
+    assert e.value.code == -3

@@ -207,6 +207,26 @@ def test_blur_parity(name, xml_dir, api, port_oracle):
     assert np.max(np.abs(got[m] - full[m]), initial=0) <= 2e-4
 
 
+def test_banded_blur_equals_full_blur(api):
+    """rdc_gaussian_blur_band: horizontal pass only on the band plus the rows its vertical pass can reach."""
+    import torch
+
+    h, w = 90, 70
+    img = torch.rand((h, w, 4), dtype=torch.float32, device="cuda")
+    sigma = torch.rand((h, w), dtype=torch.float32, device="cuda") * 4.0
+    sigma[sigma < 1.0] = 0.0
+    s = torch.cuda.current_stream().cuda_stream
+    full, scratch = torch.zeros_like(img), torch.zeros_like(img)
+    api.gaussian_blur(full.data_ptr(), img.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), w, h, 0, h, 0, s)
+    halo = int(np.ceil(3 * 4.0))
+    parts = torch.zeros_like(img)
+    for b, e in ((0, 31), (31, 60), (60, 90)):
+        scratch2 = torch.full_like(img, float("nan"))  # rows outside band + halo must never be read
+        api.gaussian_blur_band(parts.data_ptr(), img.data_ptr(), sigma.data_ptr(), scratch2.data_ptr(), w, h, b, e, halo, 0, s)
+    torch.cuda.synchronize()
+    assert torch.equal(parts.view(torch.int32), full.view(torch.int32))
+
+
 def test_reference_named_helpers(api):
     import torch
 
