@@ -47,6 +47,12 @@ clean:
 
 .PHONY: all oracle sass clean
 
+# kernel-tuning variants (not shipped): make variantd NAME=w4 DEFS=-DRDC_LOCAL_WORDS=4 -> build/librdc_b200_w4.so
+variantd:
+	@mkdir -p $(BUILD)/v$(NAME)
+	for f in $(CU_SRCS); do $(NVCC) $(NVFLAGS) $(DEFS) -c $$f -o $(BUILD)/v$(NAME)/$$(basename $$f).o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o $(BUILD)/librdc_b200_$(NAME).so $(BUILD)/v$(NAME)/*.o $(CPP_OBJS)
+
 # kernel-tuning variants (not shipped): make variant MINB=3 -> build/librdc_b200_mb3.so
 variant:
 	@mkdir -p $(BUILD)/v$(MINB)

@@ -355,7 +355,7 @@ def main():
     roofline = None
     if rank == 0:
         # work per ray from the counting build (one frame)
-        stats = torch.zeros((4,), dtype=torch.int64, device=dev)
+        stats = torch.zeros((6,), dtype=torch.int64, device=dev)
         def my_share(step):
             q = params_for(step, 0, height)
             if world > 1:
@@ -367,7 +367,8 @@ def main():
         p.stats = stats.data_ptr()
         scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
         torch.cuda.synchronize()
-        traced, nodes, chords, shaded = [float(x) for x in stats.cpu().tolist()]
+        traced, nodes, chords, shaded, deferred, gathered = [float(x) for x in stats.cpu().tolist()]
+        nodes += gathered
         band_rays = float(my_rows) * width * rpp
         n_node, n_seg, n_hit = nodes / band_rays, chords / band_rays, shaded / band_rays
         f_ray = F_GEN + n_node * F_NODE + n_seg * F_SEG + n_hit * F_SHADE + F_ACC
@@ -408,7 +409,8 @@ def main():
             "issue_slots": NCU_CAPTURE.get(args.workload) if world == 1 else None,
             "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
             "kernel_ms": kernel_ms, "flops_per_ray": f_ray,
-            "per_ray": {"nodes": n_node, "chords": n_seg, "hits_shaded": n_hit, "rays_traced": traced / band_rays},
+            "per_ray": {"nodes": n_node, "chords": n_seg, "hits_shaded": n_hit, "rays_traced": traced / band_rays,
+                        "deferred_to_tree": deferred / band_rays, "table_query_nodes": gathered / band_rays},
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                     "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; measured DRAM traffic is ~4x that "

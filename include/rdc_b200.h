@@ -126,10 +126,12 @@ typedef struct rdc_frame_params {
                                            ray's first hit, 0xFFFFFFFF for a miss (parity tests)       */
   float* max_sigma;                     /* optional device float: atomically raised to the largest
                                            blur_map value written (lets the blur skip all-zero maps)   */
-  unsigned long long* stats;            /* optional device uint64[4], atomically increased by: rays traced
-                                           (continuations included), tree nodes visited, chords tested,
-                                           hits shaded. Selects a slower counting build of the kernel;
-                                           feeds the roofline's work-per-ray figure      */
+  unsigned long long* stats;            /* optional device uint64[6], atomically increased by: rays traced
+                                           (continuations included), boxes tested (tree nodes and table
+                                           slots), chords tested, hits shaded, primary rays the local run
+                                           table deferred to the tree, nodes visited by the table queries.
+                                           Selects a slower counting build of the kernel; feeds the
+                                           roofline's work-per-ray figure                */
 } rdc_frame_params;
 
 void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t height, float rays_per_pixel);

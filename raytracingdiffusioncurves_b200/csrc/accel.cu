@@ -237,9 +237,25 @@ __global__ void k_fit_boxes(const float4* leaf_box, int n, float pad, const int*
   }
 }
 
-__global__ void k_pad_boxes(const float4* leaf_box, uint32_t n, float pad, float4* out) {
+// Also sums the padded boxes' widths and heights (fixed point, 1/1024: integer atomics keep the sums — and
+// everything derived from them — independent of the order of arrival) for the render's local-table radius.
+__global__ void k_pad_boxes(const float4* leaf_box, uint32_t n, float pad, float4* out, unsigned long long* extent_sums) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = padded(leaf_box[i], pad);
+  unsigned long long w = 0, h = 0;
+  if (i < n) {
+    const float4 b = padded(leaf_box[i], pad);
+    out[i] = b;
+    w = (unsigned long long)fminf((b.z - b.x) * 1024.0f, 4e18f);
+    h = (unsigned long long)fminf((b.w - b.y) * 1024.0f, 4e18f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    w += __shfl_down_sync(0xFFFFFFFFu, w, o);
+    h += __shfl_down_sync(0xFFFFFFFFu, h, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(extent_sums, w);
+    atomicAdd(extent_sums + 1, h);
+  }
 }
 
 __global__ void k_single_leaf_root(const float4* leaf_box, float pad, BvhNode* nodes) {
@@ -508,6 +524,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   uint32_t* run_counts = up.alloc<uint32_t>(nseg + 1);
   uint32_t* run_base = up.alloc<uint32_t>(nseg + 1);
   unsigned int* max_depth = up.alloc<unsigned int>(1);
+  unsigned long long* extent_sums = up.alloc<unsigned long long>(2);
   if (up.status) return fail(up.status);
   const float inf = std::numeric_limits<float>::infinity();
   Bounds init{inf, inf, -inf, -inf};
@@ -592,7 +609,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   k_gather_runs<<<blocks_for(n_runs), kThreads, 0, stream>>>(order, runs_in, ids_in, box_in, n_runs, runs, run_ids, leaf_box);
   TEMP_CUDA(cudaGetLastError());
 
-  k_pad_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, n_runs, pad, run_box);
+  TEMP_CUDA(cudaMemsetAsync(extent_sums, 0, 2 * sizeof(unsigned long long), stream));
+  k_pad_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, n_runs, pad, run_box, extent_sums);
   TEMP_CUDA(cudaGetLastError());
   TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
   if (n_runs == 1) {
@@ -608,6 +626,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     TEMP_CUDA(cudaGetLastError());
   }
   unsigned int depth = 0;
+  unsigned long long h_extent[2] = {0, 0};
+  TEMP_CUDA(cudaMemcpyAsync(h_extent, extent_sums, sizeof h_extent, cudaMemcpyDeviceToHost, stream));
   TEMP_CUDA(cudaMemcpyAsync(&depth, max_depth, sizeof depth, cudaMemcpyDeviceToHost, stream));
   TEMP_CUDA(cudaStreamSynchronize(stream));
   free_temps();
@@ -637,6 +657,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   s->info.has_portals = portals ? 1 : 0;
   s->info.traversal_bytes = (uint64_t)n_nodes * sizeof(BvhNode) + (uint64_t)n_runs * sizeof(RunRecord);
   s->info.pad = pad;
+  s->mean_run_w = (float)((double)h_extent[0] / 1024.0 / n_runs);
+  s->mean_run_h = (float)((double)h_extent[1] / 1024.0 / n_runs);
   *out = s;
   return 0;
 #undef BUILD_CUDA

@@ -85,7 +85,8 @@ struct rdc_scene {
   uint32_t base_dirs_capacity = 0;
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
   unsigned int* work_counters = nullptr;  // k_render's tile counter pair (one render in flight per handle)
-  uint32_t grid_blocks[16] = {};  // SM-filling grid size per kernel variant
+  uint32_t grid_blocks[32] = {};  // SM-filling grid size per kernel variant
+  float mean_run_w = 0.0f, mean_run_h = 0.0f;  // mean padded run box (local-table radius estimate)
   // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
   float4* part_rgbw = nullptr;
   float* part_blur = nullptr;

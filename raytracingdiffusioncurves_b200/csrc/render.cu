@@ -14,6 +14,7 @@
 //     (contributes zero, DeviceCode.cu:185-192) and is not generated at all (pixel_cull);
 //   * tree culling only uses conservative box tests; the accepted hit is the lexicographic minimum of
 //     (t, chord id) over all chords, the same rule the brute-force oracle applies.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -33,6 +34,28 @@ constexpr int kStack = 64;
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
 constexpr size_t kSmemSceneLimit = 40 * 1024;  // stage nodes + runs in shared memory below this
 constexpr int kRunVec = sizeof(RunRecord) / 16;
+// local run table (scenes too large for the whole-scene table): per warp, the runs around the tile
+#ifndef RDC_LOCAL_WORDS
+#define RDC_LOCAL_WORDS 2
+#endif
+constexpr int kTableWords = 2;                    // whole-scene table: 64 slots, two per lane
+constexpr int kLocalWords = RDC_LOCAL_WORDS;      // local table: 32 slots per word, one slot of each word per lane
+constexpr int kLocalSlots = 32 * kLocalWords;
+constexpr int kGatherCap = 2 * kLocalSlots;       // runs a neighbourhood query may return / nodes pending in it (at most 256)
+constexpr int kGatherAttempts = 6;                // radius adjustments per work unit
+constexpr int kDeferCap = 64;                     // deferred rays a warp can hold (a batch of 32 leaves when 32 are waiting)
+constexpr int kRingWords = kGatherCap > 2 * kDeferCap ? kGatherCap : 2 * kDeferCap;
+static_assert(kGatherCap <= 256, "candidate keys carry the position in their low 8 bits");
+enum { kModeTree = 0, kModeTable = 1, kModeLocal = 2 };
+
+struct __align__(16) WarpLocal {
+  float4 box[kLocalSlots];        // padded box of the run in each slot; slots are sorted by distance from the tile
+  uint32_t run[kLocalSlots];      // its position in Morton order
+  float dist[kLocalSlots];        // lower bound of its distance from any origin in the tile
+  uint32_t cand_run[kGatherCap];  // neighbourhood query: runs found ...
+  uint32_t cand_key[kGatherCap];  // ... and their sort keys: distance bits with the position in the low byte
+  uint32_t ring[kRingWords];      // query: nodes pending; ray loop: queue of deferred rays {lane << 16 | ray, bound}
+};
 
 struct RenderArgs {
   DevScene sc;
@@ -45,6 +68,7 @@ struct RenderArgs {
   uint32_t width, height, row_begin, row_end;
   uint32_t strip_stride, strip_offset;  // rows are dealt out in strips of kStripRows: strip t belongs to t % stride == offset
   uint32_t local_rows;                  // rows of the output buffers this launch covers
+  uint32_t row_skew;                    // row_begin % 4 of a contiguous band: tiles stay aligned to the full frame's
   uint32_t split;                       // work units per tile: unit q traces rays i = q (mod split)
   float4* part_rgbw;                    // [split][local pixels] partial sums of units (split > 1)
   float* part_blur;
@@ -56,6 +80,7 @@ struct RenderArgs {
   float zoom, off_x, off_y;
   uint32_t frame, seed;
   int orzan, use_aa, max_depth, brute, cull;
+  float local_r0;  // local table: first radius tried around a tile
 };
 
 struct Hit {
@@ -74,7 +99,7 @@ struct Accel {
 
 // per-thread work counters of the counting build (rdc_frame_params::stats)
 struct Counters {
-  unsigned int rays = 0, nodes = 0, chords = 0, shaded = 0;
+  unsigned int rays = 0, nodes = 0, chords = 0, shaded = 0, deferred = 0, gathered = 0;
 };
 
 template <bool SMEM>
@@ -138,14 +163,23 @@ __device__ __noinline__ void brute_force(const Accel& ac, float ox, float oy, fl
   for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
 }
 
-// Closest chord among the runs named by two bit masks (runs 0..31 and 32..63): the per-tile run table's
-// replacement for the tree on small scenes. Primary rays only. The run that the lane's previous ray hit
-// goes first — neighbouring strata mostly hit the same run — which gives a tight bound early; every other
-// candidate first has to pass the slab test of its padded box against that bound (the same conservative
-// test the tree applies to a leaf's box), and most do not.
-template <bool PORTALS, bool STATS>
-__device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint32_t m1, int& last_run, float ox, float oy, float dx,
-                                             float dy, Counters& cnt) {
+// Closest chord among the table slots named by two bit masks (slots 0..31 and 32..63): the replacement for
+// the tree walk of primary rays. Whole-scene table (small scenes): slot = run. Local table: slot -> run
+// through the warp's WarpLocal. The slot that the lane's previous ray hit goes first — neighbouring
+// strata mostly hit the same run — which gives a tight bound early; every other candidate first has to
+// pass the slab test of its padded box against that bound (the same conservative test the tree applies
+// to a leaf's box), and most do not. Returns the hit with leaf = run.
+template <int W>
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&m)[W], int w) {
+  uint32_t v = m[0];
+#pragma unroll
+  for (int k = 1; k < W; ++k) v = w == k ? m[k] : v;
+  return v;
+}
+
+template <bool SMEM, bool PORTALS, bool STATS, bool LOCAL, int W>
+__device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* wl, uint32_t (&m)[W], int& last_slot, float ox,
+                                             float oy, float dx, float dy, Counters& cnt) {
   Hit h;
   if (STATS) cnt.rays++;
   h.t = __int_as_float(0x7f800000);
@@ -153,35 +187,54 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint3
   h.leaf = -1;
   h.j = 0;
   h.id = kMiss;
-  if (last_run >= 0) {
-    const uint32_t bit = 1u << (last_run & 31);
-    uint32_t& m = last_run < 32 ? m0 : m1;
-    if (m & bit) {
-      m &= ~bit;
-      const int looked = test_run<true, PORTALS>(ac, last_run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+  int best_slot = -1;
+  uint32_t rest = 0u;
+  if (last_slot >= 0) {
+    const uint32_t bit = 1u << (last_slot & 31);
+    const int word = last_slot >> 5;
+    bool there = false;
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      if (word == k && (m[k] & bit)) {
+        m[k] &= ~bit;
+        there = true;
+      }
+    if (there) {
+      const int run = LOCAL ? (int)wl->run[last_slot] : last_slot;
+      const int looked = test_run<SMEM, PORTALS>(ac, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
       if (STATS) cnt.chords += looked;
+      if (h.leaf >= 0) best_slot = last_slot;
     }
   }
-  if ((m0 | m1) != 0u) {
+#pragma unroll
+  for (int k = 0; k < W; ++k) rest |= m[k];
+  if (rest != 0u) {
     const float idx = slab_rcp(dx), idy = slab_rcp(dy);
+    bool open = true;  // local table: slots come in order of distance — once one lies beyond the hit, all the rest do
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      uint32_t m = half ? m1 : m0;
-      while (m) {
-        const int r = __ffs(m) - 1 + 32 * half;
-        m &= m - 1;
-        const float4 b = ac.run_box[r];
+    for (int w = 0; w < W && open; ++w) {
+      uint32_t mw = pick_word<W>(m, w);
+      while (mw) {
+        const int slot = __ffs(mw) - 1 + 32 * w;
+        mw &= mw - 1;
+        if (LOCAL && wl->dist[slot] > h.t) {
+          open = false;
+          break;
+        }
+        const float4 b = LOCAL ? wl->box[slot] : ac.run_box[slot];
         float te;
         const float tn = rdc_slab(ox, oy, idx, idy, b.x, b.y, b.z, b.w, &te);
         if (STATS) cnt.nodes++;
         if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
-          const int looked = test_run<true, PORTALS>(ac, r, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+          const int run = LOCAL ? (int)wl->run[slot] : slot;
+          const int looked = test_run<SMEM, PORTALS>(ac, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
           if (STATS) cnt.chords += looked;
+          if (h.leaf == run) best_slot = slot;
         }
       }
     }
   }
-  if (h.leaf >= 0) last_run = h.leaf;
+  if (best_slot >= 0) last_slot = best_slot;
   return h;
 }
 
@@ -189,13 +242,14 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, uint32_t m0, uint3
 // a per-thread stack together with its entry distance, so that a subtree that lies behind a hit found in
 // the meantime is dropped when it is popped, without fetching it. A child is entered when the ray's
 // interval inside its box starts before the best hit so far (with RDC_CULL_SLACK). Leaves go through the
-// same loop (one leaf-test site keeps the kernel inside the instruction cache).
+// same loop (one leaf-test site keeps the kernel inside the instruction cache). `bound`: nothing farther
+// than this can be the answer (a deferred ray of the local table already has a candidate).
 template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
-                                             bool primary, uint32_t skip_lo, uint32_t skip_hi, Counters& cnt) {
+                                             bool primary, uint32_t skip_lo, uint32_t skip_hi, float bound, Counters& cnt) {
   Hit h;
   if (STATS) cnt.rays++;
-  h.t = __int_as_float(0x7f800000);
+  h.t = bound;  // +inf, or the distance of a hit already known (that hit is found again: ties go to the smaller id)
   h.s = 0.0f;
   h.leaf = -1;
   h.j = 0;
@@ -279,24 +333,19 @@ struct Sample {
   float r, g, b, w, blur;
 };
 
-// One primary ray through any number of portals (DeviceCode.cu:194-342, iteratively).
+// Shades a primary ray whose closest hit `h` is known and follows it through any number of portals
+// (DeviceCode.cu:194-342, iteratively; continuation rays use the tree).
 // Carried state: F = product of portal filters, Bp = product of portal blurs, S = sum of 1/w_portal;
 // terminal hit: rgb = F*rgb_T, blur = Bp*blur_T, w = 1/(1/w_T + S) — the closed form of the reference's
 // recursion w = 1/(1/w' + 1/w_here) (:310).
-template <bool SMEM, bool PORTALS, bool STATS, bool TABLE>
-__device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac, float ox, float oy, float dx, float dy,
-                                            uint32_t m0, uint32_t m1, int& last_run, uint32_t& first_hit, Counters& cnt) {
+template <bool SMEM, bool PORTALS, bool STATS>
+__device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& ac, Hit h, float ox, float oy, float dx, float dy,
+                                             Counters& cnt) {
   const DevScene& sc = a.sc;
   Sample out{0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   float Fr = 1.0f, Fg = 1.0f, Fb = 1.0f, Bp = 1.0f, S = 0.0f;
   int depth = 0;
-  uint32_t skip_lo = 1, skip_hi = 0;  // empty range
-  first_hit = kMiss;
   for (;;) {
-    Hit h;
-    if (TABLE && depth == 0) h = table_closest<PORTALS, STATS>(ac, m0, m1, last_run, ox, oy, dx, dy, cnt);
-    else h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, depth == 0, skip_lo, skip_hi, cnt);
-    if (depth == 0) first_hit = h.id;
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
     if (STATS) cnt.shaded++;
     const uint4 id = __ldg(sc.run_ids + h.leaf);  // first chord id, segment, k of the first chord, K
@@ -348,9 +397,9 @@ __device__ __forceinline__ Sample trace_ray(const RenderArgs& a, const Accel& ac
         const int Kt = (int)__ldg(sc.seg_chord_count + tseg);
         rdc_portal_skip(u, Kt, &klo, &khi);
         const uint32_t tbase = __ldg(sc.seg_chord_base + tseg);
-        skip_lo = tbase + (uint32_t)klo;
-        skip_hi = tbase + (uint32_t)khi;
         ox = o2.x; oy = o2.y; dx = ndx; dy = ndy;
+        h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, false, tbase + (uint32_t)klo, tbase + (uint32_t)khi,
+                                                __int_as_float(0x7f800000), cnt);
         continue;
       }
     }
@@ -480,15 +529,162 @@ __device__ __forceinline__ bool pixel_cull(const RenderArgs& a, float bx, float 
   return angular_interval(a.sc.root_box, bx - jit, bx + jit, by - jit, by + jit, n, first, span);
 }
 
+// Origin and direction of primary ray i of a pixel (DeviceCode.cu:110-136): tabulated base direction,
+// Philox draws in the reference's order (angle, x jitter, y jitter: :120,135,136).
+__device__ __forceinline__ void gen_ray(const RenderArgs& a, uint32_t pixel, float base_x, float base_y, int i, bool small_angle,
+                                        float& ox, float& oy, float& dx, float& dy) {
+  const float2 base = __ldg(a.base_dirs + i);
+  const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
+  ox = base_x; oy = base_y; dx = base.x; dy = base.y;
+  if (a.use_aa) {
+    float js, jc;
+    const float ang = a.two_over_n * rdc_u01(rnd.x);
+    if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
+    else sincospi_general(ang, &js, &jc);
+    dx = base.x * jc - base.y * js;
+    dy = base.x * js + base.y * jc;
+    ox = base_x + rdc_u01(rnd.y) * a.zoom;
+    oy = base_y + rdc_u01(rnd.z) * a.zoom;
+  }
+}
+
+// Largest axis gap between a box and the rectangle of origins [ox0,ox1]x[oy0,oy1]: a lower bound of the
+// distance from any origin in the rectangle to any point of the box (0 when they overlap).
+__device__ __forceinline__ float box_gap(float4 b, float ox0, float ox1, float oy0, float oy1) {
+  return fmaxf(fmaxf(fmaxf(b.x - ox1, ox0 - b.z), fmaxf(b.y - oy1, oy0 - b.w)), 0.0f);
+}
+
+struct LocalInfo {
+  uint32_t n_slots;
+  float radius;  // every run closer to the tile than this is in the table; +inf: the table holds the whole scene
+};
+
+// Local run table of a tile: the warp walks the tree breadth-first, 32 pending nodes per round, and collects
+// the runs whose padded box comes closer than R to the tile's rectangle of origins (box_gap < R). The nearest
+// kLocalSlots of them, sorted by that distance, become the table; its radius is R when all fit and the distance
+// of the nearest run left out otherwise. A walk that overflows its buffers is repeated with a smaller R, one
+// that finds less than half a table with a larger one. Everything here is a function of the tile and the scene
+// only — no timing, no neighbours — so the table, and with it the order in which a pixel's rays are summed, is
+// reproducible.
+template <bool SMEM, bool STATS>
+__device__ __forceinline__ LocalInfo gather_local(const Accel& ac, float ox0, float ox1, float oy0, float oy1, float r0,
+                                                  WarpLocal* wlp, uint32_t lane, Counters& cnt) {
+  WarpLocal& wl = *wlp;
+  const uint32_t below = (1u << lane) - 1u;
+  const float inf = __int_as_float(0x7f800000);
+  constexpr int kPer = kGatherCap / 32;  // candidates a lane looks after
+  // stored distances stay clear of the rounding of the gaps and of |D| = 1 (a hit's t is its distance only up to those)
+  const float margin = 1e-5f * (fabsf(ox0) + fabsf(ox1) + fabsf(oy0) + fabsf(oy1)) + 1e-6f;
+  float R = r0;
+  bool may_grow = true;
+#pragma unroll 1
+  for (int attempt = 0; attempt < kGatherAttempts; ++attempt) {
+    uint32_t head = 0, tail = 1, found = 0;
+    bool overflow = false;
+    if (lane == 0) wl.ring[0] = 0u;
+    __syncwarp();
+#pragma unroll 1
+    while (head < tail) {
+      const uint32_t idx = head + lane;
+      int left = 0, right = 0;
+      float dl = inf, dr = inf;
+      if (idx < tail) {
+        const float4* np = reinterpret_cast<const float4*>(ac.nodes + wl.ring[idx % kGatherCap]);
+        const float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1), ch = load16<SMEM>(np + 2);
+        left = __float_as_int(ch.x);
+        right = __float_as_int(ch.y);
+        dl = box_gap(lb, ox0, ox1, oy0, oy1);
+        dr = box_gap(rb, ox0, ox1, oy0, oy1);
+        if (STATS) cnt.gathered++;
+      }
+      head = min(head + 32u, tail);
+      const bool okl = dl < R, okr = dr < R;
+      const uint32_t inner_l = __ballot_sync(0xFFFFFFFFu, okl && left >= 0), inner_r = __ballot_sync(0xFFFFFFFFu, okr && right >= 0);
+      const uint32_t leaf_l = __ballot_sync(0xFFFFFFFFu, okl && left < 0), leaf_r = __ballot_sync(0xFFFFFFFFu, okr && right < 0);
+      const uint32_t n_inner = __popc(inner_l) + __popc(inner_r), n_leaf = __popc(leaf_l) + __popc(leaf_r);
+      if (tail - head + n_inner > (uint32_t)kGatherCap || found + n_leaf > (uint32_t)kGatherCap) {
+        overflow = true;
+        break;
+      }
+      __syncwarp();  // this round's nodes have been read: their ring entries may be overwritten
+      if (okl) {
+        if (left >= 0) wl.ring[(tail + __popc(inner_l & below)) % kGatherCap] = (uint32_t)left;
+        else {
+          const uint32_t at = found + __popc(leaf_l & below);
+          wl.cand_run[at] = (uint32_t)~left;
+          wl.cand_key[at] = (__float_as_uint(dl) & ~0xFFu) | at;  // gaps are >= 0: their bit patterns sort like the values
+        }
+      }
+      if (okr) {
+        if (right >= 0) wl.ring[(tail + __popc(inner_l) + __popc(inner_r & below)) % kGatherCap] = (uint32_t)right;
+        else {
+          const uint32_t at = found + __popc(leaf_l) + __popc(leaf_r & below);
+          wl.cand_run[at] = (uint32_t)~right;
+          wl.cand_key[at] = (__float_as_uint(dr) & ~0xFFu) | at;
+        }
+      }
+      tail += n_inner;
+      found += n_leaf;
+      __syncwarp();
+    }
+    const bool last_try = attempt == kGatherAttempts - 1;
+    if (overflow) {
+      __syncwarp();
+      R *= 0.6f;
+      may_grow = false;
+      continue;
+    }
+    if (found < (uint32_t)kLocalSlots / 2 && may_grow && found < ac.n_runs && !last_try) {
+      R *= 2.0f;
+      continue;
+    }
+    // rank every candidate by its key: the slot it gets
+    uint32_t key[kPer], rank[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      key[k] = lane + 32u * k < found ? wl.cand_key[lane + 32u * k] : 0xFFFFFFFFu;
+      rank[k] = 0u;
+    }
+#pragma unroll 2
+    for (uint32_t j = 0; j < found; ++j) {
+      const uint32_t kj = wl.cand_key[j];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) rank[k] += kj < key[k] ? 1u : 0u;
+    }
+    float radius = R;
+    if (found > (uint32_t)kLocalSlots) {  // the nearest run that is left out bounds the table
+      uint32_t edge = 0u;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)
+        if (rank[k] == (uint32_t)kLocalSlots && lane + 32u * k < found) edge = key[k] & ~0xFFu;
+      radius = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, edge));
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (lane + 32u * k < found && rank[k] < (uint32_t)kLocalSlots) {
+        const uint32_t run = wl.cand_run[lane + 32u * k];
+        wl.run[rank[k]] = run;
+        wl.dist[rank[k]] = fmaxf(__uint_as_float(key[k] & ~0xFFu) * 0.9999f - margin, 0.0f);
+        wl.box[rank[k]] = __ldg(ac.run_box + run);
+      }
+    __syncwarp();
+    const uint32_t n_slots = min(found, (uint32_t)kLocalSlots);
+    return LocalInfo{n_slots, n_slots == ac.n_runs ? inf : radius};
+  }
+  return LocalInfo{0u, 0.0f};  // too dense for a table at any radius tried: every ray goes to the tree
+}
+
 #ifndef RDC_MIN_BLOCKS
 #define RDC_MIN_BLOCKS 4  // resident blocks per SM the register allocation aims for
 #endif
 
-template <bool SMEM, bool PORTALS, bool STATS, bool TABLE>
+template <bool SMEM, bool PORTALS, bool STATS, int MODE>
 __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderArgs a) {
+  constexpr bool TABLE = MODE == kModeTable, LOCAL = MODE == kModeLocal;
   extern __shared__ uint4 smem[];
   Accel ac;
   ac.n_runs = a.sc.n_runs;
+  uint32_t smem_words = 0;  // 16-byte words of dynamic shared memory handed out so far
   if (SMEM) {
     const uint32_t node_words = a.sc.n_nodes * (uint32_t)(sizeof(BvhNode) / 16);
     const uint32_t run_words = a.sc.n_runs * (uint32_t)kRunVec;
@@ -502,11 +698,13 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.nodes = reinterpret_cast<const BvhNode*>(smem);
     ac.runs = reinterpret_cast<const float4*>(smem + node_words);
     ac.run_box = a.sc.run_box;
+    smem_words = node_words + run_words;
     if (TABLE) {
       const uint4* gb = reinterpret_cast<const uint4*>(a.sc.run_box);
 #pragma unroll 1
-      for (uint32_t i = threadIdx.x; i < a.sc.n_runs; i += kBlock) smem[node_words + run_words + i] = __ldg(gb + i);
-      ac.run_box = reinterpret_cast<const float4*>(smem + node_words + run_words);
+      for (uint32_t i = threadIdx.x; i < a.sc.n_runs; i += kBlock) smem[smem_words + i] = __ldg(gb + i);
+      ac.run_box = reinterpret_cast<const float4*>(smem + smem_words);
+      smem_words += a.sc.n_runs;
     }
     __syncthreads();
   } else {
@@ -514,6 +712,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
     ac.run_box = a.sc.run_box;
   }
+  // local table: one WarpLocal per warp behind the staged scene
+  WarpLocal* const wl = LOCAL ? reinterpret_cast<WarpLocal*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
 
   // Persistent warps: every warp of the (SM-filling) grid keeps fetching work units from one global
   // counter until the image is done. A tile is 8x4 pixels, one lane per pixel, all lanes on the same ray
@@ -525,9 +725,13 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   // makes the result independent of timing and of how the frame is divided among GPUs.
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
-  const uint32_t n_units = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH) * a.split;
+  // Tiles are cut on the full frame's grid (rows 0-3, 4-7, ...) whatever band this launch renders: a tile's run
+  // table, and with it the order in which its pixels' rays are summed, must not depend on the band.
+  const uint32_t n_units = tiles_x * ((a.local_rows + a.row_skew + kWarpTileH - 1) / kWarpTileH) * a.split;
+  const uint32_t row_origin = a.row_begin - a.row_skew;
   const size_t part_stride = (size_t)a.local_rows * a.width;
   const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
+  const float inf = __int_as_float(0x7f800000);
   float sigma_max = 0.0f;
   Counters cnt;
   for (;;) {
@@ -537,11 +741,11 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     if (unit >= n_units) break;
     const uint32_t tile = unit / a.split, q = unit % a.split;
     const uint32_t ix = (tile % tiles_x) * kWarpTileW + lane % kWarpTileW;
-    const uint32_t ly = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local)
-    // row of the full image: contiguous band, or strip (ly / 16) of this rank's interleaved share
-    const uint32_t iy = a.row_begin + ((ly / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly % kStripRows;
-    const bool valid = ix < a.width && iy < a.row_end;
-    const size_t local_pixel = (size_t)ly * a.width + ix;
+    const uint32_t vy = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local) + skew
+    // row of the full image: contiguous band, or strip (vy / 16) of this rank's interleaved share
+    const uint32_t iy = row_origin + ((vy / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + vy % kStripRows;
+    const bool valid = ix < a.width && iy >= a.row_begin && iy < a.row_end;
+    const size_t local_pixel = (size_t)(vy - a.row_skew) * a.width + ix;
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, blur = 0.0f, weight_total = 0.0f;
     // DeviceCode.cu:103-107 (unsigned arithmetic, then a signed cast)
     const float base_x = (float)(int)(ix - (a.width / 2)) * a.zoom + a.off_x;
@@ -549,26 +753,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
                                  : (float)(int)(iy - (a.height / 2)) * a.zoom + a.off_y;
     const uint32_t pixel = iy * a.width + ix;  // global pixel index: split-independent random numbers
 
-    int last_run = -1;  // run table: the run this lane's previous ray hit
-    // one primary ray: generate, trace, shade, accumulate
-    auto do_ray = [&](int i, uint32_t m0, uint32_t m1) {
-      const float2 base = __ldg(a.base_dirs + i);
-      // draw order of the reference: angle, x jitter, y jitter (DeviceCode.cu:120,135,136)
-      const rdc_u4 rnd = rdc_philox4x32_10(pixel, (uint32_t)i, 0u, 0u, a.seed, a.frame);
-      float ox = base_x, oy = base_y, dx = base.x, dy = base.y;
-      if (a.use_aa) {
-        float js, jc;
-        const float ang = a.two_over_n * rdc_u01(rnd.x);
-        if (small_angle) rdc_sincospi_kernel(ang, &js, &jc);
-        else sincospi_general(ang, &js, &jc);
-        dx = base.x * jc - base.y * js;
-        dy = base.x * js + base.y * jc;
-        ox = base_x + rdc_u01(rnd.y) * a.zoom;
-        oy = base_y + rdc_u01(rnd.z) * a.zoom;
-      }
-      uint32_t first_hit;
-      Sample s = trace_ray<SMEM, PORTALS, STATS, TABLE>(a, ac, ox, oy, dx, dy, m0, m1, last_run, first_hit, cnt);
-      if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = first_hit;
+    // adds one ray's sample to the pixel's sums (DeviceCode.cu:153-160)
+    auto accumulate = [&](const Sample& s) {
       weight_total += s.w;
       cr += s.r * s.w;
       cg += s.g * s.w;
@@ -576,13 +762,18 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       blur += s.blur * s.w;
     };
 
-    if (TABLE) {
-      // Per-tile run table (scenes of at most 64 runs): lane L works out, once per unit, under which ray
-      // indices runs L and L+32 can be seen from anywhere in the tile (all 32 pixels, jitter included).
-      // A ballot then tells every lane which runs ray i has to be tested against — usually one or two, and
-      // none at all for most rays of a sparse scene, which are then never generated. No tree walk.
+    if (TABLE || LOCAL) {
+      // Run table: lane L works out, once per unit, under which ray indices the runs in slots L and L+32 can
+      // be seen from anywhere in the tile (all 32 pixels, jitter included). A ballot then tells every lane
+      // which slots ray i has to be tested against — usually one or two, and none at all for most rays of a
+      // sparse scene, which are then never generated. No tree walk.
+      //  * whole-scene table (at most 64 runs): slot = run, every ray is settled by the table;
+      //  * local table (larger scenes): the slots hold the runs within `radius` of the tile (gather_local).
+      //    A hit closer than the radius is final — no run outside the table has a point that close. Any other
+      //    ray (farther hit, or none) is deferred: queued and, 32 at a time, sent through the tree with its
+      //    hit distance as the bound, one deferred ray per lane.
       const uint32_t tx0 = (tile % tiles_x) * kWarpTileW, ly0 = (tile / tiles_x) * kWarpTileH;
-      const uint32_t gy0 = a.row_begin + ((ly0 / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly0 % kStripRows;
+      const uint32_t gy0 = row_origin + ((ly0 / kStripRows) * a.strip_stride + a.strip_offset) * kStripRows + ly0 % kStripRows;
       const float xa = (float)(int)(tx0 - (a.width / 2)) * a.zoom + a.off_x;
       const float xb = (float)(int)(tx0 + (kWarpTileW - 1) - (a.width / 2)) * a.zoom + a.off_x;
       const float ya = a.orzan ? (float)(int)((a.height - gy0) - (a.height / 2)) * a.zoom + a.off_y
@@ -591,39 +782,167 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
                                : (float)(int)((gy0 + kWarpTileH - 1) - (a.height / 2)) * a.zoom + a.off_y;
       const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
       const float ox0 = fminf(xa, xb) - jit, ox1 = fmaxf(xa, xb) + jit, oy0 = fminf(ya, yb) - jit, oy1 = fmaxf(ya, yb) + jit;
-      int first0 = 0, span0 = -1, first1 = 0, span1 = -1;  // span -1: never, n-1: always
-      if (lane < ac.n_runs && !angular_interval(ac.run_box[lane], ox0, ox1, oy0, oy1, a.n_iter, first0, span0)) {
-        first0 = 0; span0 = a.n_iter - 1;
-      }
-      if (lane + 32 < ac.n_runs && !angular_interval(ac.run_box[lane + 32], ox0, ox1, oy0, oy1, a.n_iter, first1, span1)) {
-        first1 = 0; span1 = a.n_iter - 1;
-      }
-      // Which of this unit's rays (i = q + j*split) fall into the interval of run L / L+32: one bit per
-      // iteration j, 32 iterations at a time. The OR over all lanes lists the iterations that have any
-      // candidate run; only those are visited.
       const int n = a.n_iter, split = (int)a.split, shift = 31 - __clz(split);
-      const int n_it = (int)q < n ? (n - 1 - (int)q) / split + 1 : 0;
+      uint32_t n_slots = ac.n_runs;
+      float settle_below = inf;  // local table: a hit closer than this is final
+      bool complete = true;      // the table holds every run: a miss is final, too
+      int first_root = 0, span_root = -1;  // local table: the rays that can reach the scene at all
+      if (LOCAL) {
+        const LocalInfo li = gather_local<SMEM, STATS>(ac, ox0, ox1, oy0, oy1, a.local_r0, wl, lane, cnt);
+        n_slots = li.n_slots;
+        complete = li.radius == inf;
+        // a hit's t is its distance up to the rounding of |D| = 1 and of the box gaps: keep clear of both
+        const float mag = fabsf(ox0) + fabsf(ox1) + fabsf(oy0) + fabsf(oy1);
+        settle_below = li.radius * 0.9999f - (1e-5f * mag + 1e-6f);
+        if (!complete && !angular_interval(a.sc.root_box, ox0, ox1, oy0, oy1, n, first_root, span_root)) {
+          first_root = 0; span_root = n - 1;
+        }
+      }
+      constexpr int W = LOCAL ? kLocalWords : kTableWords;  // lane L looks after slots L, L+32, ...
+      int first[W], span[W];                                  // span -1: never, n-1: always
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        first[k] = 0; span[k] = -1;
+        if (lane + 32u * k < n_slots &&
+            !angular_interval(LOCAL ? wl->box[lane + 32 * k] : ac.run_box[lane + 32 * k], ox0, ox1, oy0, oy1, n, first[k], span[k])) {
+          first[k] = 0; span[k] = n - 1;
+        }
+      }
+      int last_slot = -1;       // the slot this lane's previous ray hit
+      uint32_t queued = 0;      // deferred rays waiting in wl->ring
+      // Deferred samples are summed apart from the direct ones and added at the end of the unit: when a batch
+      // leaves depends on the other pixels of the tile (a band may cut some off), the two sums do not.
+      float dr = 0.0f, dg = 0.0f, db = 0.0f, dw = 0.0f, dblur = 0.0f;
+
+      // Up to 32 deferred rays, one per lane: regenerate the ray (owner's pixel, ray index), closest chord by the
+      // tree under the known bound, shade; then the owners add the samples in queue order.
+      auto flush = [&]() {
+        const uint32_t batch = min(queued, 32u);
+        uint32_t entry = 0;
+        float bound = 0.0f;
+        if (lane < batch) {
+          entry = wl->ring[2 * lane];
+          bound = __uint_as_float(wl->ring[2 * lane + 1]);
+        }
+        uint32_t move0 = 0, move1 = 0;
+        const bool moves = lane + 32 < queued;
+        if (moves) {
+          move0 = wl->ring[2 * (lane + 32)];
+          move1 = wl->ring[2 * (lane + 32) + 1];
+        }
+        __syncwarp();
+        if (moves) {
+          wl->ring[2 * lane] = move0;
+          wl->ring[2 * lane + 1] = move1;
+        }
+        __syncwarp();
+        queued -= batch;
+        const uint32_t owner = entry >> 16;
+        const int i = (int)(entry & 0xFFFFu);
+        const uint32_t o_pixel = __shfl_sync(0xFFFFFFFFu, pixel, owner);
+        const float o_bx = __shfl_sync(0xFFFFFFFFu, base_x, owner), o_by = __shfl_sync(0xFFFFFFFFu, base_y, owner);
+        const uint32_t o_local = __shfl_sync(0xFFFFFFFFu, (uint32_t)local_pixel, owner);
+        float pr = 0.0f, pg = 0.0f, pb = 0.0f, pw = 0.0f, pblur = 0.0f;
+        if (lane < batch) {
+          if (STATS) cnt.deferred++;
+          float ox, oy, dx, dy;
+          gen_ray(a, o_pixel, o_bx, o_by, i, small_angle, ox, oy, dx, dy);
+          const Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, false, ox, oy, dx, dy, true, 1u, 0u, bound, cnt);
+          if (a.hit_ids) a.hit_ids[(size_t)o_local * (size_t)n + i] = h.id;
+          const Sample s = trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt);
+          pw = s.w; pr = s.r * s.w; pg = s.g * s.w; pb = s.b * s.w; pblur = s.blur * s.w;
+        }
 #pragma unroll 1
-      for (int cb = 0; cb < n_it; cb += 32) {
-        const int here = min(32, n_it - cb);
-        const uint32_t it0 = iteration_mask(first0, span0, (int)q, shift, cb, here, n);
-        const uint32_t it1 = iteration_mask(first1, span1, (int)q, shift, cb, here, n);
-        uint32_t any = __reduce_or_sync(0xFFFFFFFFu, it0 | it1);
-        if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
-          uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
-          while (none) {
-            const int j = __ffs(none) - 1;
-            none &= none - 1;
-            a.hit_ids[local_pixel * (size_t)n + (q + ((cb + j) << shift))] = kMiss;
+        for (uint32_t k = 0; k < batch; ++k) {
+          const uint32_t o = __shfl_sync(0xFFFFFFFFu, owner, k);
+          const float w = __shfl_sync(0xFFFFFFFFu, pw, k), r = __shfl_sync(0xFFFFFFFFu, pr, k);
+          const float g = __shfl_sync(0xFFFFFFFFu, pg, k), b = __shfl_sync(0xFFFFFFFFu, pb, k);
+          const float bl = __shfl_sync(0xFFFFFFFFu, pblur, k);
+          if (lane == o) {
+            dw += w;
+            dr += r; dg += g; db += b;
+            dblur += bl;
           }
         }
-        while (any) {
+      };
+
+      // Which of this unit's rays (i = q + j*split) fall into the interval of the runs in slots L / L+32: one
+      // bit per iteration j, 32 iterations at a time. The OR over all lanes lists the iterations that have any
+      // candidate (local table: or that can reach the scene beyond the table); only those are visited.
+      const int n_it = (int)q < n ? (n - 1 - (int)q) / split + 1 : 0;
+      int cb0 = -32;  // first iteration of the current chunk
+      uint32_t it[W], any = 0u;
+#pragma unroll 1
+      for (;;) {
+        while (any == 0u && cb0 + 32 < n_it) {  // next chunk of 32 iterations
+          cb0 += 32;
+          const int here = min(32, n_it - cb0);
+          uint32_t mine = 0u;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            it[k] = iteration_mask(first[k], span[k], (int)q, shift, cb0, here, n);
+            mine |= it[k];
+          }
+          any = __reduce_or_sync(0xFFFFFFFFu, mine);
+          if (LOCAL) any |= iteration_mask(first_root, span_root, (int)q, shift, cb0, here, n);
+          if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
+            uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
+            while (none) {
+              const int j = __ffs(none) - 1;
+              none &= none - 1;
+              a.hit_ids[local_pixel * (size_t)n + (q + ((cb0 + j) << shift))] = kMiss;
+            }
+          }
+        }
+        const bool done = any == 0u;
+        if (!done) {
           const int j = __ffs(any) - 1;
           any &= any - 1;
-          const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (it0 >> j) & 1u);
-          const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (it1 >> j) & 1u);
-          if (valid) do_ray((int)q + ((cb + j) << shift), m0, m1);
+          uint32_t m[W], m_any = 0u;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            m[k] = __ballot_sync(0xFFFFFFFFu, (it[k] >> j) & 1u);
+            m_any |= m[k];
+          }
+          const int i = (int)q + ((cb0 + j) << shift);
+          bool defer = false;
+          float bound = inf;
+          if (valid) {
+            float ox, oy, dx, dy;
+            gen_ray(a, pixel, base_x, base_y, i, small_angle, ox, oy, dx, dy);
+            Hit h;
+            if (!LOCAL || m_any != 0u) {
+              h = table_closest<SMEM, PORTALS, STATS, LOCAL, W>(ac, wl, m, last_slot, ox, oy, dx, dy, cnt);
+            } else {
+              h.t = inf; h.s = 0.0f; h.leaf = -1; h.j = 0; h.id = kMiss;
+            }
+            if (LOCAL && !(h.leaf >= 0 ? h.t < settle_below : complete)) {
+              defer = true;
+              bound = h.t;
+            } else {
+              if (a.hit_ids) a.hit_ids[local_pixel * (size_t)n + i] = h.id;
+              accumulate(trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt));
+            }
+          }
+          if (LOCAL) {
+            const uint32_t votes = __ballot_sync(0xFFFFFFFFu, defer);
+            if (defer) {
+              const uint32_t at = queued + __popc(votes & ((1u << lane) - 1u));
+              wl->ring[2 * at] = (lane << 16) | (uint32_t)i;  // at < kDeferCap: at most 31 wait when up to 32 arrive
+              wl->ring[2 * at + 1] = __float_as_uint(bound);
+            }
+            queued += __popc(votes);
+            __syncwarp();
+          }
         }
+        // one site for the deferred rays: a full batch, or whatever is left when the unit ends
+        if (LOCAL && (queued >= 32u || (done && queued > 0u))) flush();
+        if (done) break;
+      }
+      if (LOCAL) {
+        weight_total += dw;
+        cr += dr; cg += dg; cb += db;
+        blur += dblur;
       }
     } else if (valid) {
       // Ray indices that can reach the scene: [lo0,hi0] and (when the angular range wraps) [lo1,hi1],
@@ -651,7 +970,13 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         const int lo = part ? lo1 : lo0, hi = part ? hi1 : hi0;
         // first index >= lo that belongs to this unit
         int i = lo + (int)((q + a.split - (uint32_t)lo % a.split) % a.split);
-        for (; i <= hi; i += (int)a.split) do_ray(i, 0u, 0u);
+        for (; i <= hi; i += (int)a.split) {
+          float ox, oy, dx, dy;
+          gen_ray(a, pixel, base_x, base_y, i, small_angle, ox, oy, dx, dy);
+          const Hit h = closest_chord<SMEM, PORTALS, STATS>(ac, a.brute != 0, ox, oy, dx, dy, true, 1u, 0u, inf, cnt);
+          if (a.hit_ids) a.hit_ids[local_pixel * (size_t)a.n_iter + i] = h.id;
+          accumulate(trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt));
+        }
       }
     }
     bool finish = true;
@@ -697,11 +1022,14 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   if (STATS) {
     unsigned int r = __reduce_add_sync(0xFFFFFFFFu, cnt.rays), n = __reduce_add_sync(0xFFFFFFFFu, cnt.nodes);
     unsigned int c = __reduce_add_sync(0xFFFFFFFFu, cnt.chords), h = __reduce_add_sync(0xFFFFFFFFu, cnt.shaded);
+    unsigned int d = __reduce_add_sync(0xFFFFFFFFu, cnt.deferred), g = __reduce_add_sync(0xFFFFFFFFu, cnt.gathered);
     if (lane == 0) {
       atomicAdd(a.stats + 0, (unsigned long long)r);
       atomicAdd(a.stats + 1, (unsigned long long)n);
       atomicAdd(a.stats + 2, (unsigned long long)c);
       atomicAdd(a.stats + 3, (unsigned long long)h);
+      atomicAdd(a.stats + 4, (unsigned long long)d);
+      atomicAdd(a.stats + 5, (unsigned long long)g);
     }
   }
   // the last warp to leave rewinds the tile counter for the next launch on this handle
@@ -788,28 +1116,62 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const uint32_t my_strips = a.strip_offset < strips ? (strips - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
   if (my_strips == 0) return 0;
   a.local_rows = a.strip_stride > 1 ? my_strips * kStripRows : rows;
+  a.row_skew = a.strip_stride > 1 ? 0u : p.row_begin % kWarpTileH;  // strips: give row_begin as a multiple of 4 for split-independent bits
   a.work = s->work_counters;
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   const bool smem = scene_bytes <= kSmemSceneLimit;
   const bool portals = s->info.has_portals != 0;
-  // Per-tile run table instead of the tree for primary rays: small scenes, whole number of rays >= 8, LBVH mode.
-  const bool table = smem && s->dev.n_runs <= kTableRuns && (float)n_iter == p.number_of_rays_per_pixel && n_iter >= 8 &&
-                     !a.brute && getenv("RDC_B200_NO_TABLE") == nullptr;
-  const size_t dyn = smem ? scene_bytes + (table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0;
-  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 run table
-  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (table ? 8 : 0);
+  // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
+  const bool masks_ok = (float)n_iter == p.number_of_rays_per_pixel && n_iter >= 8 && !a.brute;
+  //  * the whole scene in one table: at most 64 runs;
+  const bool table = masks_ok && smem && s->dev.n_runs <= kTableRuns && getenv("RDC_B200_NO_TABLE") == nullptr;
+  //  * a table per tile of the runs around it: larger scenes, unless the view is zoomed out so far that a tile's
+  //    own footprint already meets more runs than the table holds. First radius: the one at which a scene of
+  //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
+  //    mean run box w x h; the kernel adapts it per tile.
+  bool local = false;
+  if (masks_ok && !table && s->dev.n_runs > kTableRuns && getenv("RDC_B200_NO_LOCAL") == nullptr) {
+    const float4 rb = s->dev.root_box;
+    const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
+    const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;
+    const double pa = (kWarpTileW - 1) * z + 2 * jit + s->mean_run_w, pb = (kWarpTileH - 1) * z + 2 * jit + s->mean_run_h;
+    const double per_run = area / s->dev.n_runs;  // scene area per run
+    if (area > 0.0 && pa * pb < 0.5 * kLocalSlots * per_run) {
+      const double disc = (pa + pb) * (pa + pb) - 4.0 * (pa * pb - 1.25 * kLocalSlots * per_run);
+      a.local_r0 = (float)((std::sqrt(disc) - (pa + pb)) * 0.25);
+      local = a.local_r0 > 0.0f && std::isfinite(a.local_r0);
+    }
+  }
+  if (const char* env = getenv("RDC_B200_LOCAL_R0")) {  // tuning experiments only
+    const float v = (float)atof(env);
+    if (local && v > 0.0f) a.local_r0 = v;
+  }
+  const size_t dyn = (smem ? scene_bytes + (table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
+                     (local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0);
+  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table
+  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (table ? 8 : 0) | (local ? 16 : 0);
   void (*kernel)(RenderArgs) = nullptr;
   switch (variant) {
-    case 0: kernel = k_render<false, false, false, false>; break;
-    case 1: kernel = k_render<true, false, false, false>; break;
-    case 2: kernel = k_render<false, true, false, false>; break;
-    case 3: kernel = k_render<true, true, false, false>; break;
-    case 6: kernel = k_render<false, true, true, false>; break;
-    case 7: kernel = k_render<true, true, true, false>; break;
-    case 9: kernel = k_render<true, false, false, true>; break;
-    case 11: kernel = k_render<true, true, false, true>; break;
-    default: kernel = k_render<true, true, true, true>; break;  // 15
+    case 0: kernel = k_render<false, false, false, kModeTree>; break;
+    case 1: kernel = k_render<true, false, false, kModeTree>; break;
+    case 2: kernel = k_render<false, true, false, kModeTree>; break;
+    case 3: kernel = k_render<true, true, false, kModeTree>; break;
+    case 6: kernel = k_render<false, true, true, kModeTree>; break;
+    case 7: kernel = k_render<true, true, true, kModeTree>; break;
+    case 9: kernel = k_render<true, false, false, kModeTable>; break;
+    case 11: kernel = k_render<true, true, false, kModeTable>; break;
+    case 15: kernel = k_render<true, true, true, kModeTable>; break;
+    case 16: kernel = k_render<false, false, false, kModeLocal>; break;
+    case 17: kernel = k_render<true, false, false, kModeLocal>; break;
+    case 18: kernel = k_render<false, true, false, kModeLocal>; break;
+    case 19: kernel = k_render<true, true, false, kModeLocal>; break;
+    case 22: kernel = k_render<false, true, true, kModeLocal>; break;
+    case 23: kernel = k_render<true, true, true, kModeLocal>; break;
+    default:
+      set_error("render: no kernel variant %d", variant);
+      return RDC_E_INVALID;
   }
+  if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
     int per_sm = 0, sms = 0;
     RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
@@ -829,10 +1191,11 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     int v = atoi(env);
     if (v == 1 || v == 2 || v == 4) split = (uint32_t)v;
   }
-  while (split > 1 && ((uint32_t)n_iter < 16 * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
+  // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
+  while (split > 1 && ((uint32_t)n_iter < (local ? 64u : 16u) * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
   a.split = split;
   const size_t local_pixels = (size_t)a.local_rows * p.image_width;
-  const uint32_t local_tiles = tiles_x * ((a.local_rows + kWarpTileH - 1) / kWarpTileH);
+  const uint32_t local_tiles = tiles_x * ((a.local_rows + a.row_skew + kWarpTileH - 1) / kWarpTileH);
   if (split > 1 && (local_pixels * split > s->part_capacity || local_tiles > s->tile_capacity)) {
     RDC_CUDA(cudaStreamSynchronize(stream));
     cudaFree(s->part_rgbw);

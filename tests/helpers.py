@@ -49,7 +49,7 @@ class GpuRenderer:
         self.host = api.HostScene.from_xml_file(xml_path, api.default_ingest_options(use_diffusion_curve_save=int(orzan)))
         self.scene = api.Scene(self.host.arrays, accel, torch.cuda.current_stream().cuda_stream)
 
-    def render(self, params, want_hits=False, blur=False, use_flag=True):
+    def render(self, params, want_hits=False, blur=False, use_flag=True, want_stats=False):
         torch, api = self.torch, self.api
         rows = params.row_end - params.row_begin
         w = params.image_width
@@ -61,6 +61,8 @@ class GpuRenderer:
         flag = torch.zeros((1,), dtype=torch.float32, device=dev)
         params.hit_ids = hits.data_ptr() if want_hits else None
         params.max_sigma = flag.data_ptr() if use_flag else None
+        stats = torch.zeros((6,), dtype=torch.int64, device=dev) if want_stats else None
+        params.stats = stats.data_ptr() if want_stats else None  # selects the counting build of the kernel
         stream = torch.cuda.current_stream().cuda_stream
         self.scene.render(params, image.data_ptr(), sigma.data_ptr(), stream)
         blurred = None
@@ -76,6 +78,8 @@ class GpuRenderer:
             "hits": hits.cpu().numpy().view(np.uint32) if want_hits else None,
             "blurred": blurred.cpu().numpy() if blur else None,
             "max_sigma": float(flag.item()),
+            # rays traced, boxes tested, chords tested, hits shaded, rays deferred to the tree, nodes visited by table queries
+            "stats": stats.cpu().tolist() if want_stats else None,
         }
         return out
 

@@ -305,6 +305,60 @@ def test_synthetic_scene_global_memory_path(api, port_oracle, tmp_path):
     compare_images(out["image"], oimg, RGB_TOL)
 
 
+LOCAL_VIEWS = [("DiffusionCurvePack/dolphin.xml", 0.25, 0.0, 0.0, 16), ("DiffusionCurvePack/dolphin.xml", 0.5, 60.0, -40.0, 16),
+               ("DiffusionCurvePack/dolphin.xml", 2.0, 0.0, 0.0, 8), ("DiffusionCurvePack/lady_bug.xml", 1.0, -30.0, 20.0, 24),
+               ("DiffusionCurvePack/zephyr.xml", 0.125, 10.0, 10.0, 16), ("DiffusionCurvePack/face.xml", 0.3, -20.0, 35.0, 40),
+               ("DiffusionCurvePack/roses_spirales.xml", 0.75, 0.0, 0.0, 16)]
+
+
+@pytest.mark.parametrize("name,zoom,off_x,off_y,n", LOCAL_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[1]}" for v in LOCAL_VIEWS])
+def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle):
+    """Close-up views of the larger scenes: primary rays settled by the per-tile table of nearby runs, the rest
+    deferred to the tree — every first hit still the oracle's brute-force closest chord."""
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    w, h = 72, 52  # not a multiple of the 8x4 tile
+    p = po.make_params(w, h, n, zoom_factor=zoom, offset_x=off_x, offset_y=off_y)
+    oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+    r = GpuRenderer(path)
+    out = r.render(product_params(api, p), want_hits=True)
+    assert np.array_equal(out["hits"], ohits)
+    compare_images(out["image"], oimg, RGB_TOL)
+    brute = r.render(product_params(api, po.make_params(w, h, n, zoom_factor=zoom, offset_x=off_x, offset_y=off_y,
+                                                        traversal=api.TRAVERSAL_BRUTE_FORCE)), want_hits=True)
+    assert np.array_equal(out["hits"], brute["hits"])
+    counted = r.render(product_params(api, p), want_hits=True, want_stats=True)
+    assert np.array_equal(counted["hits"], ohits)
+    traced, _, _, _, deferred, gathered = counted["stats"]
+    print(f"{name} zoom {zoom}: {traced} rays traced, {deferred} deferred to the tree, {gathered} nodes visited by table queries")
+    if zoom <= 1.0:
+        assert gathered > 0, "the local run table was not used"
+        assert deferred < traced
+
+
+def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path):
+    """Config 5 in miniature at its own scale (one pixel = one scene unit): the local-table path on a dense scene."""
+    xml = api.synth_xml(3000, 1024, 1024)
+    f = tmp_path / "synth.xml"
+    f.write_bytes(xml)
+    scene = po.ingest_xml(str(f), True)
+    r = GpuRenderer(str(f))
+    for off_x, off_y, n in ((0.0, 0.0, 16), (300.0, -250.0, 32), (-480.0, 470.0, 8)):
+        p = po.make_params(64, 48, n, zoom_factor=1.0, offset_x=off_x, offset_y=off_y)
+        oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+        out = r.render(product_params(api, p), want_hits=True, want_stats=True)
+        assert np.array_equal(out["hits"], ohits)
+        compare_images(out["image"], oimg, RGB_TOL)
+        traced, _, _, _, deferred, gathered = out["stats"]
+        assert gathered > 0 and deferred < traced
+        plain = r.render(product_params(api, p), want_hits=True)
+        assert np.array_equal(plain["hits"], ohits)
+        # the same frame in two bands: bit-identical pixels (the table depends on the tile only)
+        parts = [r.render(product_params(api, po.make_params(64, 48, n, zoom_factor=1.0, offset_x=off_x, offset_y=off_y,
+                                                               row_begin=b, row_end=e))) for b, e in ((0, 16), (16, 48))]
+        assert np.array_equal(bits(np.concatenate([q["image"] for q in parts])), bits(plain["image"]))
+
+
 def test_accumulate_is_a_running_mean(api):
     import torch
 

@@ -15,6 +15,9 @@ def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     spec, width, height, rpp, depth = bench.WORKLOADS[workload]
+    # RDC_PROFILE_SIZE=WxHxN: same scene and framing, smaller frame (keeps ncu replays short)
+    if os.environ.get("RDC_PROFILE_SIZE"):
+        width, height, rpp = (int(v) for v in os.environ["RDC_PROFILE_SIZE"].split("x"))
     zoom = bench.workload_zoom(spec, height)
     kind, payload = bench.scene_source(spec)
     host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
@@ -37,6 +40,16 @@ def main():
         t1.record()
         torch.cuda.synchronize()
         print(f"frame {f}: {t0.elapsed_time(t1):.3f} ms, chords {scene.stats.n_chords}, max sigma {flag.item():.3f}")
+    if os.environ.get("RDC_PROFILE_STATS"):
+        stats = torch.zeros((6,), dtype=torch.int64, device="cuda")
+        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=0)
+        p.stats = stats.data_ptr()
+        scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
+        torch.cuda.synchronize()
+        rays = float(width) * height * rpp
+        names = ("traced", "boxes", "chords", "shaded", "deferred", "query_nodes")
+        print("per primary ray: " + ", ".join(f"{k} {v / rays:.4f}" for k, v in zip(names, stats.cpu().tolist())) +
+              f"; runs {scene.stats.n_runs}")
 
 
 if __name__ == "__main__":
