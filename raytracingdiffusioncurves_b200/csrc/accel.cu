@@ -536,7 +536,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   // Leaf size: long runs make a shallow tree (good when curves are sparse: few boxes overlap), short runs
   // keep leaf boxes tight (good when curves are dense). Mean chord spacing ~ extent / sqrt(#chords).
   uint32_t run_len = (uint32_t)o.run_length;
-  if (o.run_length <= 0) run_len = n_chords <= 4096 ? 8 : n_chords <= 65536 ? 4 : 2;
+  if (o.run_length <= 0) run_len = n_chords <= 4096 ? 8 : 4;
   if (run_len > RDC_RUN) run_len = RDC_RUN;
   k_run_counts<<<blocks_for(nseg), kThreads, 0, stream>>>(counts, nseg, run_len, run_counts);
   BUILD_CUDA(cudaGetLastError());

@@ -55,6 +55,7 @@ struct __align__(16) WarpLocal {
   uint32_t cand_run[kGatherCap];  // neighbourhood query: runs found ...
   uint32_t cand_key[kGatherCap];  // ... and their sort keys: distance bits with the position in the low byte
   uint32_t ring[kRingWords];      // query: nodes pending; ray loop: queue of deferred rays {lane << 16 | ray, bound}
+  // (copying the slots' run records in here as well was measured: 10-15 % slower — fewer resident blocks)
 };
 
 struct RenderArgs {
@@ -121,9 +122,8 @@ __device__ __forceinline__ float slab_rcp(float d) {
 // the chords whose end points lie on different sides of the ray; the (rare) marked ones are then resolved
 // in a rolled loop that re-reads their two points — same inputs, same operations, same bits.
 template <bool SMEM, bool PORTALS>
-__device__ __forceinline__ int test_run(const Accel& ac, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
+__device__ __forceinline__ int test_run(const float4* rp, int leaf, float ox, float oy, float dx, float dy, float inv_dd,
                                         uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
-  const float4* rp = ac.runs + (size_t)leaf * kRunVec;
   const float4 head = load16<SMEM>(rp);
   const int count = (int)__float_as_uint(head.y);
   // bit k of `above`: point k lies on the positive side of the ray's supporting line
@@ -160,7 +160,7 @@ __device__ __forceinline__ int test_run(const Accel& ac, int leaf, float ox, flo
 template <bool SMEM, bool PORTALS>
 __device__ __noinline__ void brute_force(const Accel& ac, float ox, float oy, float dx, float dy, float inv_dd,
                                          uint32_t skip_lo, uint32_t skip_hi, Hit& h) {
-  for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+  for (uint32_t r = 0; r < ac.n_runs; ++r) test_run<SMEM, PORTALS>(ac.runs + (size_t)r * kRunVec, (int)r, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
 }
 
 // Closest chord among the table slots named by two bit masks (slots 0..31 and 32..63): the replacement for
@@ -201,7 +201,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
       }
     if (there) {
       const int run = LOCAL ? (int)wl->run[last_slot] : last_slot;
-      const int looked = test_run<SMEM, PORTALS>(ac, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+      const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
       if (STATS) cnt.chords += looked;
       if (h.leaf >= 0) best_slot = last_slot;
     }
@@ -227,7 +227,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
         if (STATS) cnt.nodes++;
         if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
           const int run = LOCAL ? (int)wl->run[slot] : slot;
-          const int looked = test_run<SMEM, PORTALS>(ac, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+          const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
           if (STATS) cnt.chords += looked;
           if (h.leaf == run) best_slot = slot;
         }
@@ -266,7 +266,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   int node = 0;
   for (;;) {
     if (node < 0) {
-      const int looked = test_run<SMEM, PORTALS>(ac, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+      const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)(~node) * kRunVec, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
       if (STATS) cnt.chords += looked;
     } else {
       if (STATS) cnt.nodes++;
@@ -1130,7 +1130,9 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
   //    mean run box w x h; the kernel adapts it per tile.
   bool local = false;
-  if (masks_ok && !table && s->dev.n_runs > kTableRuns && getenv("RDC_B200_NO_LOCAL") == nullptr) {
+  uint32_t local_min_runs = 1024;  // measured on the bundled scenes: below this the tree is as fast or faster
+  if (const char* env = getenv("RDC_B200_LOCAL_MIN_RUNS")) local_min_runs = (uint32_t)atoi(env);  // tuning experiments only
+  if (masks_ok && !table && s->dev.n_runs >= local_min_runs && s->dev.n_runs > kTableRuns && getenv("RDC_B200_NO_LOCAL") == nullptr) {
     const float4 rb = s->dev.root_box;
     const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
     const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;

@@ -312,9 +312,10 @@ LOCAL_VIEWS = [("DiffusionCurvePack/dolphin.xml", 0.25, 0.0, 0.0, 16), ("Diffusi
 
 
 @pytest.mark.parametrize("name,zoom,off_x,off_y,n", LOCAL_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[1]}" for v in LOCAL_VIEWS])
-def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle):
+def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle, monkeypatch):
     """Close-up views of the larger scenes: primary rays settled by the per-tile table of nearby runs, the rest
     deferred to the tree — every first hit still the oracle's brute-force closest chord."""
+    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")  # the library keeps scenes this small on the tree (it is faster there)
     path = os.path.join(xml_dir, name)
     scene = po.ingest_xml(path, True)
     w, h = 72, 52  # not a multiple of the 8x4 tile
@@ -336,8 +337,9 @@ def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_o
         assert deferred < traced
 
 
-def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path):
+def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path, monkeypatch):
     """Config 5 in miniature at its own scale (one pixel = one scene unit): the local-table path on a dense scene."""
+    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")
     xml = api.synth_xml(3000, 1024, 1024)
     f = tmp_path / "synth.xml"
     f.write_bytes(xml)

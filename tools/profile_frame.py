@@ -24,29 +24,39 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     run_length = int(os.environ.get("RDC_RUN_LENGTH", "0"))
     scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length), stream)
-    image = torch.empty((height, width, 4), dtype=torch.float32, device="cuda")
-    sigma = torch.empty((height, width), dtype=torch.float32, device="cuda")
+    # RDC_PROFILE_ROWS=a:b: only that band of the frame (full-size frames of the largest workloads take seconds)
+    row_begin, row_end = 0, height
+    if os.environ.get("RDC_PROFILE_ROWS"):
+        row_begin, row_end = (int(v) for v in os.environ["RDC_PROFILE_ROWS"].split(":"))
+    rows = row_end - row_begin
+    image = torch.empty((rows, width, 4), dtype=torch.float32, device="cuda")
+    sigma = torch.empty((rows, width), dtype=torch.float32, device="cuda")
     scratch = torch.empty_like(image)
     flag = torch.zeros((1,), dtype=torch.float32, device="cuda")
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     for f in range(frames):
         flag.zero_()
-        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=f)
+        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=f, row_begin=row_begin,
+                                     row_end=row_end)
         p.max_sigma = flag.data_ptr()
         t0.record()
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
-        api.gaussian_blur(image.data_ptr(), image.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), width, height, 0, height,
-                          flag.data_ptr(), stream)
         t1.record()
+        api.gaussian_blur(image.data_ptr(), image.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), width, rows, 0, rows,
+                          flag.data_ptr(), stream)
+        t2.record()
         torch.cuda.synchronize()
-        print(f"frame {f}: {t0.elapsed_time(t1):.3f} ms, chords {scene.stats.n_chords}, max sigma {flag.item():.3f}")
+        ms = t0.elapsed_time(t2)
+        print(f"frame {f}: {ms:.3f} ms (render {t0.elapsed_time(t1):.3f}, blur {t1.elapsed_time(t2):.3f}), "
+              f"{rows * width * rpp / ms / 1e6:.2f} Grays/s, chords {scene.stats.n_chords}, max sigma {flag.item():.3f}")
     if os.environ.get("RDC_PROFILE_STATS"):
         stats = torch.zeros((6,), dtype=torch.int64, device="cuda")
-        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=0)
+        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=0, row_begin=row_begin,
+                                     row_end=row_end)
         p.stats = stats.data_ptr()
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
         torch.cuda.synchronize()
-        rays = float(width) * height * rpp
+        rays = float(width) * rows * rpp
         names = ("traced", "boxes", "chords", "shaded", "deferred", "query_nodes")
         print("per primary ray: " + ", ".join(f"{k} {v / rays:.4f}" for k, v in zip(names, stats.cpu().tolist())) +
               f"; runs {scene.stats.n_runs}")
