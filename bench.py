@@ -270,10 +270,27 @@ def main():
         bands = rd.FrameBuffers(plan, dev)
         render_strips, blur_rows = api.cuda_callbacks(scene, lambda: params_for(step_box[0], 0, height), stream)
         band, sigma_band = bands.local_image, bands.local_sigma
+        # Peer-memory form (render kernel stores into the consumers' frames over NVLink, no NCCL on the data path) unless
+        # symmetric memory is unavailable on this box or RDC_BENCH_NCCL=1 asks for the NCCL gather.
+        peers, peer_error = None, None
+        if os.environ.get("RDC_BENCH_NCCL") != "1":
+            try:
+                peers = rd.PeerFrameBuffers(plan, dev)
+                render_to, blur_rows_peer = api.cuda_peer_callbacks(scene, lambda: params_for(step_box[0], 0, height), stream)
+            except Exception as exc:  # noqa: BLE001
+                peers, peer_error = None, f"{type(exc).__name__}: {exc}"
+        ok = torch.tensor([1 if peers is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
+        if int(ok.item()) == 0:
+            peers = None
+        exchange = "peer memory (symmetric memory, stores from the render/blur kernels)" if peers is not None else \
+            "NCCL gather / all-gather" + (f" (peer path unavailable: {peer_error})" if peer_error else "")
 
         def frame_step(step):
             """One frame over all ranks: render my strips -> (all-gather, local band blur) -> gather to rank 0."""
             step_box[0] = step
+            if peers is not None:
+                return rd.render_frame_peer(peers, render_to, blur_rows_peer, use_blur=True)
             return rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
         launches_per_step = 1 + (2 if halo > 0 else 0)
 
@@ -346,7 +363,8 @@ def main():
         t_local = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
         t_e2e = float(t_local.item())
-        e2e_api = "distributed.render_frame (band render, halo exchange, blur, gather) + copy of the frame to pinned host memory on rank 0"
+        e2e_api = ("distributed.render_frame_peer" if peers is not None else "distributed.render_frame") + \
+            " (strip render, exchange, band blur, frame on rank 0) + copy of the frame to pinned host memory on rank 0"
     e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
            "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams) * world, "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
            "api": e2e_api}
@@ -429,7 +447,7 @@ def main():
             "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
             "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
                        "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
-                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"16-row strips dealt round-robin over {world} GPUs, gather to rank 0" if world > 1 else "single GPU",
+                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"16-row strips dealt round-robin over {world} GPUs, to rank 0 through {exchange}" if world > 1 else "single GPU",
                        "runs": st.n_runs, "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
             "clocks": sampler.result(),

@@ -138,6 +138,16 @@ void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t heig
 /* image = float4[rows*W] (xyz written, w = 1), blur_map = float[rows*W]; both device pointers. */
 int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream);
 
+/* Multi-GPU form (row bands / strips per GPU, gather to rank 0): renders the rows the parameters
+ * select like rdc_render, but stores every finished pixel at its place in the FULL frame — image
+ * float4[image_height*image_width], blur_map float[image_height*image_width] — of each of n_targets target frames.
+ * The pointers may address peer GPUs' memory (NVLink peer access, CUDA IPC, symmetric memory): the render kernel's
+ * stores ARE the gather. hit_ids / stats / max_sigma work as in rdc_render. Enqueue-only; the caller orders the
+ * consumers of the target frames after this call on every rank (a barrier over the ranks' streams). */
+#define RDC_MAX_FRAME_TARGETS 8
+int rdc_render_to_frames(rdc_scene* scene, const rdc_frame_params* params, uint32_t n_targets, float* const* images,
+                         float* const* blur_maps, rdc_stream stream);
+
 /* ---- helper kernels: same names and signatures as helperKernels.cu's extern "C" launchers
  *      (declared at optixHello.cpp:51-54) ---- */
 #ifndef RDC_NO_REFERENCE_HELPER_NAMES

@@ -93,6 +93,8 @@ PROTOTYPES = {
     "rdc_scene_destroy": (None, [C.c_void_p]),
     "rdc_default_frame_params": (None, [C.POINTER(FrameParams), C.c_uint32, C.c_uint32, C.c_float]),
     "rdc_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rdc_render_to_frames": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.c_void_p]),
     "gaussianBlur": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "setFloatDevice": (None, [C.c_void_p, C.c_uint, C.c_float, C.c_void_p]),
     "setupCurand": (None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -323,6 +325,14 @@ class Scene:
         _check(_lib.rdc_render(self._h, C.byref(params), C.c_void_p(image_ptr), C.c_void_p(blur_map_ptr), C.c_void_p(stream)),
                "rdc_render")
 
+    def render_to_frames(self, params: FrameParams, image_ptrs, blur_map_ptrs, stream: int = 0) -> None:
+        """Like render, but every finished pixel is stored at its place in each of the given FULL frames (device
+        addresses, peers' memory included): rdc_render_to_frames."""
+        n = len(image_ptrs)
+        images = (C.c_void_p * n)(*image_ptrs)
+        sigmas = (C.c_void_p * n)(*blur_map_ptrs)
+        _check(_lib.rdc_render_to_frames(self._h, C.byref(params), n, images, sigmas, C.c_void_p(stream)), "rdc_render_to_frames")
+
     def render_frame_to_host(self, params: FrameParams, use_blur: bool, host_image_ptr: int, stream: int = 0) -> None:
         _check(_lib.rdc_render_frame_to_host(self._h, C.byref(params), int(use_blur), C.c_void_p(host_image_ptr),
                                              C.c_void_p(stream)), "rdc_render_frame_to_host")
@@ -380,7 +390,19 @@ def cuda_callbacks(scene: "Scene", make_params, stream: int = 0):
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
 
     def blur_rows(dest, source, sigma, scratch, height, row_begin, row_end, halo):
-        gaussian_blur_band(dest.data_ptr(), source.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), source.shape[1], height,
+        dest_ptr = dest if isinstance(dest, int) else dest.data_ptr()  # an address: a frame in a peer's memory
+        gaussian_blur_band(dest_ptr, source.data_ptr(), sigma.data_ptr(), scratch.data_ptr(), source.shape[1], height,
                            row_begin, row_end, halo, 0, stream)
 
     return render_strips, blur_rows
+
+
+def cuda_peer_callbacks(scene: "Scene", make_params, stream: int = 0):
+    """(render_to, blur_rows) for distributed.render_frame_peer: the render stores straight into the target frames."""
+
+    def render_to(image_ptrs, sigma_ptrs, stride, offset):
+        p = make_params()
+        p.strip_stride, p.strip_offset = (stride, offset) if stride > 1 else (0, 0)
+        scene.render_to_frames(p, image_ptrs, sigma_ptrs, stream)
+
+    return render_to, cuda_callbacks(scene, make_params, stream)[1]

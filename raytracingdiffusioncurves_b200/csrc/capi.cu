@@ -286,6 +286,17 @@ int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, f
   });
 }
 
+int rdc_render_to_frames(rdc_scene* scene, const rdc_frame_params* params, uint32_t n_targets, float* const* images,
+                         float* const* blur_maps, rdc_stream stream) {
+  if (!scene || !params || n_targets == 0) {
+    rdc::set_error("render_to_frames: null argument or no target frame");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_INVALID, [&]() {
+    return rdc::render(scene, *params, nullptr, nullptr, (cudaStream_t)stream, n_targets, images, blur_maps);
+  });
+}
+
 int rdc_gaussian_blur(void* dest, const void* source, const float* sigma, void* scratch, int width, int height,
                       int row_begin, int row_end, const float* max_sigma, rdc_stream stream) {
   return rdc::gaussian_blur(static_cast<float4*>(dest), static_cast<const float4*>(source), sigma,

@@ -110,7 +110,8 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
 void destroy_scene(rdc_scene* s);
 int download_chords(const rdc_scene* s, float* geom, uint32_t* ids);
 // render.cu
-int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream);
+int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream, uint32_t n_targets = 0,
+           float* const* target_images = nullptr, float* const* target_blur_maps = nullptr);
 // blur.cu
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
                   int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows = -1);

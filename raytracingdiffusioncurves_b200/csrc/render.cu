@@ -82,6 +82,10 @@ struct RenderArgs {
   uint32_t frame, seed;
   int orzan, use_aa, max_depth, brute, cull;
   float local_r0;  // local table: first radius tried around a tile
+  // rdc_render_to_frames: finished pixels go to their place in up to RDC_MAX_FRAME_TARGETS FULL frames (peer memory)
+  uint32_t n_targets;
+  float4* target_image[RDC_MAX_FRAME_TARGETS];
+  float* target_blur[RDC_MAX_FRAME_TARGETS];
 };
 
 struct Hit {
@@ -203,7 +207,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
       const int run = LOCAL ? (int)wl->run[last_slot] : last_slot;
       const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
       if (STATS) cnt.chords += looked;
-      if (h.leaf >= 0) best_slot = last_slot;
+      if (LOCAL && h.leaf >= 0) best_slot = last_slot;
     }
   }
 #pragma unroll
@@ -212,7 +216,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
     const float idx = slab_rcp(dx), idy = slab_rcp(dy);
     bool open = true;  // local table: slots come in order of distance — once one lies beyond the hit, all the rest do
 #pragma unroll 1
-    for (int w = 0; w < W && open; ++w) {
+    for (int w = 0; w < W && (!LOCAL || open); ++w) {
       uint32_t mw = pick_word<W>(m, w);
       while (mw) {
         const int slot = __ffs(mw) - 1 + 32 * w;
@@ -229,12 +233,16 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
           const int run = LOCAL ? (int)wl->run[slot] : slot;
           const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
           if (STATS) cnt.chords += looked;
-          if (h.leaf == run) best_slot = slot;
+          if (LOCAL && h.leaf == run) best_slot = slot;
         }
       }
     }
   }
-  if (best_slot >= 0) last_slot = best_slot;
+  if (LOCAL) {
+    if (best_slot >= 0) last_slot = best_slot;
+  } else if (h.leaf >= 0) {
+    last_slot = h.leaf;  // whole-scene table: slot = run
+  }
   return h;
 }
 
@@ -870,74 +878,90 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       // bit per iteration j, 32 iterations at a time. The OR over all lanes lists the iterations that have any
       // candidate (local table: or that can reach the scene beyond the table); only those are visited.
       const int n_it = (int)q < n ? (n - 1 - (int)q) / split + 1 : 0;
-      int cb0 = -32;  // first iteration of the current chunk
+      int cb0 = 0;  // first iteration of the current chunk
       uint32_t it[W], any = 0u;
+      // masks of the chunk of 32 iterations that starts at cb0
+      auto open_chunk = [&]() {
+        const int here = min(32, n_it - cb0);
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          it[k] = iteration_mask(first[k], span[k], (int)q, shift, cb0, here, n);
+          mine |= it[k];
+        }
+        any = __reduce_or_sync(0xFFFFFFFFu, mine);
+        if (LOCAL) any |= iteration_mask(first_root, span_root, (int)q, shift, cb0, here, n);
+        if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
+          uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
+          while (none) {
+            const int j = __ffs(none) - 1;
+            none &= none - 1;
+            a.hit_ids[local_pixel * (size_t)n + (q + ((cb0 + j) << shift))] = kMiss;
+          }
+        }
+      };
+      // the next listed iteration of the chunk: one ray per lane
+      auto next_ray = [&]() {
+        const int j = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t m[W], m_any = 0u;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          m[k] = __ballot_sync(0xFFFFFFFFu, (it[k] >> j) & 1u);
+          m_any |= m[k];
+        }
+        const int i = (int)q + ((cb0 + j) << shift);
+        bool defer = false;
+        float bound = inf;
+        if (valid) {
+          float ox, oy, dx, dy;
+          gen_ray(a, pixel, base_x, base_y, i, small_angle, ox, oy, dx, dy);
+          Hit h;
+          if (!LOCAL || m_any != 0u) {
+            h = table_closest<SMEM, PORTALS, STATS, LOCAL, W>(ac, wl, m, last_slot, ox, oy, dx, dy, cnt);
+          } else {
+            h.t = inf; h.s = 0.0f; h.leaf = -1; h.j = 0; h.id = kMiss;
+          }
+          if (LOCAL && !(h.leaf >= 0 ? h.t < settle_below : complete)) {
+            defer = true;
+            bound = h.t;
+          } else {
+            if (a.hit_ids) a.hit_ids[local_pixel * (size_t)n + i] = h.id;
+            accumulate(trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt));
+          }
+        }
+        if (LOCAL) {
+          const uint32_t votes = __ballot_sync(0xFFFFFFFFu, defer);
+          if (defer) {
+            const uint32_t at = queued + __popc(votes & ((1u << lane) - 1u));
+            wl->ring[2 * at] = (lane << 16) | (uint32_t)i;  // at < kDeferCap: at most 31 wait when up to 32 arrive
+            wl->ring[2 * at + 1] = __float_as_uint(bound);
+          }
+          queued += __popc(votes);
+          __syncwarp();
+        }
+      };
+      if constexpr (!LOCAL) {
 #pragma unroll 1
-      for (;;) {
-        while (any == 0u && cb0 + 32 < n_it) {  // next chunk of 32 iterations
-          cb0 += 32;
-          const int here = min(32, n_it - cb0);
-          uint32_t mine = 0u;
-#pragma unroll
-          for (int k = 0; k < W; ++k) {
-            it[k] = iteration_mask(first[k], span[k], (int)q, shift, cb0, here, n);
-            mine |= it[k];
-          }
-          any = __reduce_or_sync(0xFFFFFFFFu, mine);
-          if (LOCAL) any |= iteration_mask(first_root, span_root, (int)q, shift, cb0, here, n);
-          if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
-            uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
-            while (none) {
-              const int j = __ffs(none) - 1;
-              none &= none - 1;
-              a.hit_ids[local_pixel * (size_t)n + (q + ((cb0 + j) << shift))] = kMiss;
-            }
-          }
+        for (; cb0 < n_it; cb0 += 32) {
+          open_chunk();
+          while (any) next_ray();
         }
-        const bool done = any == 0u;
-        if (!done) {
-          const int j = __ffs(any) - 1;
-          any &= any - 1;
-          uint32_t m[W], m_any = 0u;
-#pragma unroll
-          for (int k = 0; k < W; ++k) {
-            m[k] = __ballot_sync(0xFFFFFFFFu, (it[k] >> j) & 1u);
-            m_any |= m[k];
+      } else {
+        // one loop, so that the deferred rays have ONE site (the tree walk and the shading are inlined there):
+        // a full batch, or whatever is left when the unit ends
+        cb0 = -32;
+#pragma unroll 1
+        for (;;) {
+          while (any == 0u && cb0 + 32 < n_it) {
+            cb0 += 32;
+            open_chunk();
           }
-          const int i = (int)q + ((cb0 + j) << shift);
-          bool defer = false;
-          float bound = inf;
-          if (valid) {
-            float ox, oy, dx, dy;
-            gen_ray(a, pixel, base_x, base_y, i, small_angle, ox, oy, dx, dy);
-            Hit h;
-            if (!LOCAL || m_any != 0u) {
-              h = table_closest<SMEM, PORTALS, STATS, LOCAL, W>(ac, wl, m, last_slot, ox, oy, dx, dy, cnt);
-            } else {
-              h.t = inf; h.s = 0.0f; h.leaf = -1; h.j = 0; h.id = kMiss;
-            }
-            if (LOCAL && !(h.leaf >= 0 ? h.t < settle_below : complete)) {
-              defer = true;
-              bound = h.t;
-            } else {
-              if (a.hit_ids) a.hit_ids[local_pixel * (size_t)n + i] = h.id;
-              accumulate(trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt));
-            }
-          }
-          if (LOCAL) {
-            const uint32_t votes = __ballot_sync(0xFFFFFFFFu, defer);
-            if (defer) {
-              const uint32_t at = queued + __popc(votes & ((1u << lane) - 1u));
-              wl->ring[2 * at] = (lane << 16) | (uint32_t)i;  // at < kDeferCap: at most 31 wait when up to 32 arrive
-              wl->ring[2 * at + 1] = __float_as_uint(bound);
-            }
-            queued += __popc(votes);
-            __syncwarp();
-          }
+          const bool done = any == 0u;
+          if (!done) next_ray();
+          if (queued >= 32u || (done && queued > 0u)) flush();
+          if (done) break;
         }
-        // one site for the deferred rays: a full batch, or whatever is left when the unit ends
-        if (LOCAL && (queued >= 32u || (done && queued > 0u))) flush();
-        if (done) break;
       }
       if (LOCAL) {
         weight_total += dw;
@@ -1008,9 +1032,20 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     }
     if (finish && valid) {
       // all rays missed -> 0/0 = NaN, as in the reference (DeviceCode.cu:176-181); .w is set to 1
-      a.image[local_pixel] = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
+      const float4 rgb1 = make_float4(cr / weight_total, cg / weight_total, cb / weight_total, 1.0f);
       const float sigma = blur / weight_total;
-      a.blur_map[local_pixel] = sigma;
+      if (a.n_targets == 0) {
+        a.image[local_pixel] = rgb1;
+        a.blur_map[local_pixel] = sigma;
+      } else {
+        // multi-GPU: straight to the pixel's place in every target frame — stores over NVLink when the frame
+        // lives on a peer (8 pixels x 16 B = one 128-byte line per tile row), no gather afterwards
+#pragma unroll 1
+        for (uint32_t t = 0; t < a.n_targets; ++t) {
+          a.target_image[t][pixel] = rgb1;
+          a.target_blur[t][pixel] = sigma;
+        }
+      }
       sigma_max = fmaxf(sigma_max, sigma);  // NaN and negative sigmas do not raise the flag (the blur yields NaN for them either way)
     }
   }
@@ -1044,11 +1079,21 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
 
 }  // namespace
 
-int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream) {
-  if (!s || !image || !blur_map) {
+int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream, uint32_t n_targets,
+           float* const* target_images, float* const* target_blur_maps) {
+  if (!s || (n_targets == 0 && (!image || !blur_map))) {
     set_error("render: null argument");
     return RDC_E_INVALID;
   }
+  if (n_targets > RDC_MAX_FRAME_TARGETS || (n_targets > 0 && (!target_images || !target_blur_maps))) {
+    set_error("render: at most %d target frames", RDC_MAX_FRAME_TARGETS);
+    return RDC_E_INVALID;
+  }
+  for (uint32_t t = 0; t < n_targets; ++t)
+    if (!target_images[t] || !target_blur_maps[t]) {
+      set_error("render: target frame %u is null", t);
+      return RDC_E_INVALID;
+    }
   if (p.image_width == 0 || p.image_height == 0 || p.row_begin >= p.row_end || p.row_end > p.image_height) {
     set_error("render: bad image size or row band [%u,%u) of %u", p.row_begin, p.row_end, p.image_height);
     return RDC_E_INVALID;
@@ -1087,6 +1132,11 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.sc = s->dev;
   a.image = image;
   a.blur_map = blur_map;
+  a.n_targets = n_targets;
+  for (uint32_t t = 0; t < n_targets; ++t) {
+    a.target_image[t] = reinterpret_cast<float4*>(target_images[t]);
+    a.target_blur[t] = target_blur_maps[t];
+  }
   a.base_dirs = s->base_dirs;
   a.hit_ids = p.hit_ids;
   a.max_sigma = p.max_sigma;

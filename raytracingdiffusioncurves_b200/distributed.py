@@ -19,6 +19,13 @@ The data path has at most two exchange steps:
                   ceil(3*sigma_max) rows the vertical pass can reach, helperKernels.cu:65,74);
       gather      blurred bands -> rank 0
 
+On GPUs the default is the peer-memory form of the same plan (PeerFrameBuffers / render_frame_peer): the frame
+buffers are symmetric memory (every rank holds the device address of every other rank's buffer, NVLink peer
+access), and the render kernel stores each finished pixel straight into its place in the consumer's frame —
+rank 0's when the scene has no blur, everybody's when it has (the all-gather) — and the band blur stores straight
+into rank 0's finished frame. The stores ARE the collectives; what is left is one barrier over the ranks'
+streams per exchange step. The NCCL form above stays as the fallback and is what the gloo CPU tests exercise.
+
 What renders and what blurs is injected (`render_strips`, `blur_rows`): the product passes the CUDA entry
 points (api.cuda_callbacks), the CPU tests pass the oracle. This module only moves rows.
 """
@@ -146,3 +153,53 @@ def render_frame(buf: FrameBuffers, render_strips, blur_rows, use_blur: bool = T
         return None
     torch.index_select(buf.all_bands, 0, buf.band_index, out=buf.frame)
     return buf.frame
+
+
+class PeerFrameBuffers:
+    """Symmetric-memory frame buffers for render_frame_peer (GPUs of one box, NVLink peer access).
+
+    `full_image` / `full_sigma` hold the whole rendered frame (every rank has one; without blur only rank 0's is
+    written), `frame` the finished frame (meaningful on rank 0). Raises if symmetric memory is not available —
+    the caller then stays on FrameBuffers / render_frame."""
+
+    def __init__(self, plan: StripPlan, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        p = self.plan = plan
+        group = group if group is not None else dist.group.WORLD
+        f32 = dict(dtype=torch.float32, device=device)
+        self.full_image = symm.empty((p.height, p.width, 4), **f32)
+        self.full_sigma = symm.empty((p.height, p.width), **f32)
+        self.frame = symm.empty((p.height, p.width, 4), **f32)
+        self.h_image = symm.rendezvous(self.full_image, group)
+        self.h_sigma = symm.rendezvous(self.full_sigma, group)
+        self.h_frame = symm.rendezvous(self.frame, group)
+        self.image_ptrs = [int(x) for x in self.h_image.buffer_ptrs]
+        self.sigma_ptrs = [int(x) for x in self.h_sigma.buffer_ptrs]
+        self.frame_ptrs = [int(x) for x in self.h_frame.buffer_ptrs]
+        self.scratch = torch.zeros((p.height, p.width, 4), **f32) if p.halo > 0 else None
+
+    def barrier(self):
+        """All ranks' streams meet: what was enqueued before it on any rank is complete and visible after it."""
+        self.h_frame.barrier()
+
+
+def render_frame_peer(buf: PeerFrameBuffers, render_to, blur_rows, use_blur: bool = True):
+    """One frame over all ranks through peer memory. Returns the finished frame [H, W, 4] on rank 0, None elsewhere.
+
+    render_to(image_ptrs, sigma_ptrs, stride, offset): renders strips t % stride == offset and stores every pixel
+        at its place in each of the full frames addressed (rdc_render_to_frames).
+    blur_rows: as in render_frame; `dest` is a device address here (rank 0's frame)."""
+    p = buf.plan
+    blur = use_blur and p.halo > 0
+    buf.barrier()  # the consumers of the previous frame (rank 0's copy-out, the peers' blur) are done with the buffers
+    if not blur:
+        render_to([buf.frame_ptrs[0]], [buf.sigma_ptrs[0]], p.world, p.rank)
+        buf.barrier()
+        return buf.frame if p.rank == 0 else None
+    render_to(buf.image_ptrs, buf.sigma_ptrs, p.world, p.rank)  # the all-gather
+    buf.barrier()
+    b, e = p.band
+    blur_rows(buf.frame_ptrs[0], buf.full_image, buf.full_sigma, buf.scratch, p.height, b, e, p.halo)  # the gather
+    buf.barrier()
+    return buf.frame if p.rank == 0 else None

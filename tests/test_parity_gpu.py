@@ -151,6 +151,29 @@ def test_interleaved_strips_reassemble_bit_exactly(xml_dir, api):
         assert np.array_equal(bits(got_sigma), bits(full["blur_map"])), world
 
 
+def test_render_to_frames_places_strips_in_full_frames(xml_dir, api):
+    """rdc_render_to_frames (the multi-GPU form): every rank's strips stored straight into two full target frames
+    give, together, the one-call frame — bit for bit, in both targets."""
+    import torch
+
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))
+    w, h, n = 72, 83, 8
+    full = r.render(api.default_frame_params(w, h, n, zoom_factor=512 / h))
+    s = torch.cuda.current_stream().cuda_stream
+    for world in (2, 3):
+        images = [torch.full((h, w, 4), float("nan"), dtype=torch.float32, device="cuda") for _ in range(2)]
+        sigmas = [torch.full((h, w), float("nan"), dtype=torch.float32, device="cuda") for _ in range(2)]
+        for rank in range(world):
+            p = api.default_frame_params(w, h, n, zoom_factor=512 / h, strip_stride=world, strip_offset=rank)
+            r.scene.render_to_frames(p, [t.data_ptr() for t in images], [t.data_ptr() for t in sigmas], s)
+        torch.cuda.synchronize()
+        for t in range(2):
+            assert np.array_equal(bits(images[t].cpu().numpy()), bits(full["image"])), (world, t)
+            assert np.array_equal(bits(sigmas[t].cpu().numpy()), bits(full["blur_map"])), (world, t)
+    with pytest.raises(api.RdcError):
+        r.scene.render_to_frames(api.default_frame_params(w, h, n), [0], [0], s)
+
+
 def test_lbvh_equals_brute_force_at_headline_size(xml_dir, api):
     """Size-independent property at BASELINE's config 2 (arch.xml 1920x1080, 128 rays/pixel):
     the LBVH traversal and the no-tree kernel agree on every one of the 265 M first hits."""

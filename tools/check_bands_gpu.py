@@ -39,6 +39,17 @@ def main():
         render_strips, blur_rows = api.cuda_callbacks(scene, make, stream)
         frame = rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
         torch.cuda.synchronize()
+        # the same frame through peer memory (render kernel stores into the consumers' frames)
+        peer_frame, peer_note = None, "peer path unavailable"
+        try:
+            peers = rd.PeerFrameBuffers(plan, dev)
+            render_to, blur_rows_p = api.cuda_peer_callbacks(scene, make, stream)
+            for _ in range(2):  # twice: buffers are reused from frame to frame
+                peer_frame = rd.render_frame_peer(peers, render_to, blur_rows_p, use_blur=True)
+            torch.cuda.synchronize()
+            peer_note = "peer path"
+        except Exception as exc:  # noqa: BLE001
+            peer_note = f"peer path unavailable: {type(exc).__name__}: {exc}"
         if rank == 0:
             image = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
             sigma = torch.empty((h, w), dtype=torch.float32, device=dev)
@@ -53,6 +64,12 @@ def main():
             same = torch.equal(frame[:h, :, :3].contiguous().view(torch.int32), want[..., :3].contiguous().view(torch.int32))
             print(f"{'OK  ' if same else 'FAIL'} {name} {w}x{h}@{rpp} world={world} halo={halo}", flush=True)
             failures += 0 if same else 1
+            if peer_frame is not None:
+                same = torch.equal(peer_frame[..., :3].contiguous().view(torch.int32), want[..., :3].contiguous().view(torch.int32))
+                print(f"{'OK  ' if same else 'FAIL'} {name} {peer_note}", flush=True)
+                failures += 0 if same else 1
+            else:
+                print(f"SKIP {name} {peer_note}", flush=True)
         dist.barrier()
     dist.destroy_process_group()
     sys.exit(1 if failures else 0)
