@@ -9,7 +9,7 @@ A "step" is one frame of the hot path: ray generation + closest-hit traversal + 
 xmls/arch.xml at 1920x1080, 128 rays per pixel, Orzan flag / blur / per-ray jitter as shipped, denoiser
 off. The metric is Grays/s = primary rays per second (W*H*rpp / t_frame / 1e9), whole job.
 
-N > 1: the image is dealt out in 16-row strips, round-robin over the ranks (scene + tree replicated); the
+N > 1: the image is dealt out in 8-row strips, round-robin over the ranks (scene + tree replicated); the
 strips are gathered to rank 0 over NVLink (NCCL); scenes with blur all-gather the rendered frame and every
 rank blurs one contiguous band before the gather (raytracingdiffusioncurves_b200/distributed.py). Total
 work is fixed as N grows ("strong" scaling); every exchange is inside the timed region.
@@ -47,7 +47,7 @@ F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
 # From the committed `ncu --set full` capture of k_render on the headline workload
 # (profiles/r01_k_render_v7_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
 NCU_CAPTURE = {
-    "arch_1080p_128rpp": {"dram_bytes": 3.554304e6 + 156.500736e6, "issue_active": 0.8174, "source": "profiles/r01_k_render_v7_ncu_summary.txt"},
+    "arch_1080p_128rpp": {"dram_bytes": 3.698176e6 + 156.869632e6, "issue_active": 0.8236, "source": "profiles/r01b_k_render_arch_ncu_summary.txt"},
 }
 
 
@@ -286,11 +286,13 @@ def main():
         exchange = "peer memory (symmetric memory, stores from the render/blur kernels)" if peers is not None else \
             "NCCL gather / all-gather" + (f" (peer path unavailable: {peer_error})" if peer_error else "")
 
+        hook_box = [None]  # e2e: rank 0's "the copy-out of the frame before last is done" wait (see render_frame_peer)
+
         def frame_step(step):
             """One frame over all ranks: render my strips -> (all-gather, local band blur) -> gather to rank 0."""
             step_box[0] = step
             if peers is not None:
-                return rd.render_frame_peer(peers, render_to, blur_rows_peer, use_blur=True)
+                return rd.render_frame_peer(peers, render_to, blur_rows_peer, use_blur=True, before_barrier=hook_box[0])
             return rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
         launches_per_step = 1 + (2 if halo > 0 else 0)
 
@@ -348,23 +350,59 @@ def main():
         e2e_api = ("rdc_render_frame_to_host_async + rdc_frame_wait (render + blur + copy to pinned host memory, the copy of one "
                    f"frame overlapping the next frame's rendering); frame-by-frame rdc_render_frame_to_host: {t_sync * 1e3:.3f} ms")
     else:
-        def e2e_step(step):
-            frame = frame_step(step)
-            if rank == 0:
-                host_img.copy_(frame[:height], non_blocking=True)
-            torch.cuda.synchronize()
+        if peers is not None:
+            # pipelined like the single-GPU call: rank 0 copies frame f to pinned host memory on its own stream while
+            # frame f+1 is rendered into the other frame buffer; two pinned buffers in turn; the clock stops when the
+            # last frame is in host memory.
+            main, copy_stream = torch.cuda.current_stream(), torch.cuda.Stream()
+            host_imgs = [host_img, torch.empty((height, width, 4), dtype=torch.float32).pin_memory()] if rank == 0 else None
+            rendered = [torch.cuda.Event() for _ in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+            count = [0]
+
+            def wait_for_copy_before_last():
+                c = count[0]
+                if rank == 0 and c >= 1:
+                    main.wait_event(copied[(c - 1) % 2])  # frame c-1's copy-out: its buffer is the next frame's target
+            hook_box[0] = wait_for_copy_before_last
+
+            def e2e_step(step):
+                frame = frame_step(step)
+                c = count[0]
+                if rank == 0:
+                    rendered[c % 2].record(main)
+                    copy_stream.wait_event(rendered[c % 2])
+                    with torch.cuda.stream(copy_stream):
+                        host_imgs[c % 2].copy_(frame, non_blocking=True)
+                        copied[c % 2].record(copy_stream)
+                count[0] = c + 1
+
+            def e2e_finish():
+                torch.cuda.synchronize()
+        else:
+            def e2e_step(step):
+                frame = frame_step(step)
+                if rank == 0:
+                    host_img.copy_(frame[:height], non_blocking=True)
+                torch.cuda.synchronize()
+
+            def e2e_finish():
+                pass
         for s in range(2):
             e2e_step(s)
+        e2e_finish()
         barrier()
         t0 = time.perf_counter()
         for s in range(n_e2e):
             e2e_step(1000 + s)
+        e2e_finish()
         barrier()
         t_local = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
         t_e2e = float(t_local.item())
         e2e_api = ("distributed.render_frame_peer" if peers is not None else "distributed.render_frame") + \
-            " (strip render, exchange, band blur, frame on rank 0) + copy of the frame to pinned host memory on rank 0"
+            " (strip render, exchange, band blur, frame on rank 0) + copy of the frame to pinned host memory on rank 0" + \
+            (", the copy of one frame overlapping the next frame's rendering" if peers is not None else "")
     e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
            "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams) * world, "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
            "api": e2e_api}
@@ -380,7 +418,9 @@ def main():
                 q.strip_stride, q.strip_offset = world, rank
             return q
 
-        my_rows = sum(min(16, height - t * 16) for t in range(rank, (height + 15) // 16, world))
+        from raytracingdiffusioncurves_b200.distributed import STRIP as rd_strip
+
+        my_rows = sum(min(rd_strip, height - t * rd_strip) for t in range(rank, (height + rd_strip - 1) // rd_strip, world))
         p = my_share(0)
         p.stats = stats.data_ptr()
         scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
@@ -447,7 +487,7 @@ def main():
             "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
             "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
                        "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
-                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"16-row strips dealt round-robin over {world} GPUs, to rank 0 through {exchange}" if world > 1 else "single GPU",
+                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"8-row strips dealt round-robin over {world} GPUs, to rank 0 through {exchange}" if world > 1 else "single GPU",
                        "runs": st.n_runs, "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
             "clocks": sampler.result(),

@@ -102,7 +102,7 @@ void rdc_scene_destroy(rdc_scene* scene);
 /* ---- per-frame render: replaces optixLaunch(pipeline, stream, d_param, sizeof(Params), &sbt, W, H, 1)
  *      (optixHello.cpp:1184) running DeviceCode.cu:85-342 ---- */
 
-#define RDC_STRIP_ROWS 16
+#define RDC_STRIP_ROWS 8
 #define RDC_TRAVERSAL_LBVH 0
 #define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
 

@@ -4,7 +4,7 @@ One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests). Th
 replicated. Random numbers are keyed by the GLOBAL pixel index, so the assembled frame is bit-identical to
 the single-GPU frame whatever the split.
 
-Rendering is dealt out in STRIPS of 16 rows, round-robin: rank r renders strips t with t % world == r. A
+Rendering is dealt out in STRIPS of 8 rows, round-robin: rank r renders strips t with t % world == r. A
 contiguous band per rank (the obvious split) is badly balanced on sparse scenes — in arch.xml the rows that
 look into the arch cost several times the rows that look away from it — while interleaved strips sample
 every region of the image on every rank.
@@ -36,7 +36,7 @@ import math
 import torch
 import torch.distributed as dist
 
-STRIP = 16  # RDC_STRIP_ROWS (include/rdc_b200.h): the render kernel's tile height
+STRIP = 8  # RDC_STRIP_ROWS (include/rdc_b200.h): the render kernel's tile height
 
 
 def row_band(height: int, rank: int, world: int) -> tuple[int, int]:
@@ -158,8 +158,9 @@ def render_frame(buf: FrameBuffers, render_strips, blur_rows, use_blur: bool = T
 class PeerFrameBuffers:
     """Symmetric-memory frame buffers for render_frame_peer (GPUs of one box, NVLink peer access).
 
-    `full_image` / `full_sigma` hold the whole rendered frame (every rank has one; without blur only rank 0's is
-    written), `frame` the finished frame (meaningful on rank 0). Raises if symmetric memory is not available —
+    `full_image` / `full_sigma` hold the whole rendered frame (every rank has one; without blur only rank 0's
+    sigma is written), `frames` two finished frames used in turn (meaningful on rank 0) so that rank 0 can still be
+    copying frame f out while frame f+1 is rendered into the other. Raises if symmetric memory is not available —
     the caller then stays on FrameBuffers / render_frame."""
 
     def __init__(self, plan: StripPlan, device, group=None):
@@ -170,36 +171,50 @@ class PeerFrameBuffers:
         f32 = dict(dtype=torch.float32, device=device)
         self.full_image = symm.empty((p.height, p.width, 4), **f32)
         self.full_sigma = symm.empty((p.height, p.width), **f32)
-        self.frame = symm.empty((p.height, p.width, 4), **f32)
+        self.frames = [symm.empty((p.height, p.width, 4), **f32) for _ in range(2)]
         self.h_image = symm.rendezvous(self.full_image, group)
         self.h_sigma = symm.rendezvous(self.full_sigma, group)
-        self.h_frame = symm.rendezvous(self.frame, group)
+        self.h_frames = [symm.rendezvous(f, group) for f in self.frames]
         self.image_ptrs = [int(x) for x in self.h_image.buffer_ptrs]
         self.sigma_ptrs = [int(x) for x in self.h_sigma.buffer_ptrs]
-        self.frame_ptrs = [int(x) for x in self.h_frame.buffer_ptrs]
+        self.frame_ptrs = [[int(x) for x in h.buffer_ptrs] for h in self.h_frames]
         self.scratch = torch.zeros((p.height, p.width, 4), **f32) if p.halo > 0 else None
+        self.turn = 0
 
     def barrier(self):
         """All ranks' streams meet: what was enqueued before it on any rank is complete and visible after it."""
-        self.h_frame.barrier()
+        self.h_image.barrier()
 
 
-def render_frame_peer(buf: PeerFrameBuffers, render_to, blur_rows, use_blur: bool = True):
+def render_frame_peer(buf: PeerFrameBuffers, render_to, blur_rows, use_blur: bool = True, before_barrier=None):
     """One frame over all ranks through peer memory. Returns the finished frame [H, W, 4] on rank 0, None elsewhere.
 
     render_to(image_ptrs, sigma_ptrs, stride, offset): renders strips t % stride == offset and stores every pixel
         at its place in each of the full frames addressed (rdc_render_to_frames).
-    blur_rows: as in render_frame; `dest` is a device address here (rank 0's frame)."""
+    blur_rows: as in render_frame; `dest` is a device address here (rank 0's frame).
+    before_barrier(): called on every rank right before the frame's first barrier is enqueued — rank 0 makes its
+        stream wait there for whatever still reads the frame buffer the NEXT call will be written into (the frame
+        this call returned two calls ago); the peers only start that next frame after this barrier.
+
+    Buffer reuse is safe without an opening barrier: the frame of call c goes to frames[c % 2], whose last reader
+    (call c-2's consumer on rank 0) is ordered before call c-1's barrier by before_barrier; full_image / full_sigma
+    are read by the band blur of a call, which every rank finishes before that call's closing barrier."""
     p = buf.plan
     blur = use_blur and p.halo > 0
-    buf.barrier()  # the consumers of the previous frame (rank 0's copy-out, the peers' blur) are done with the buffers
+    turn = buf.turn
+    buf.turn ^= 1
+    out_ptr = buf.frame_ptrs[turn][0]
     if not blur:
-        render_to([buf.frame_ptrs[0]], [buf.sigma_ptrs[0]], p.world, p.rank)
+        render_to([out_ptr], [buf.sigma_ptrs[0]], p.world, p.rank)  # the gather
+        if before_barrier is not None:
+            before_barrier()
         buf.barrier()
-        return buf.frame if p.rank == 0 else None
+        return buf.frames[turn] if p.rank == 0 else None
     render_to(buf.image_ptrs, buf.sigma_ptrs, p.world, p.rank)  # the all-gather
+    if before_barrier is not None:
+        before_barrier()
     buf.barrier()
     b, e = p.band
-    blur_rows(buf.frame_ptrs[0], buf.full_image, buf.full_sigma, buf.scratch, p.height, b, e, p.halo)  # the gather
+    blur_rows(out_ptr, buf.full_image, buf.full_sigma, buf.scratch, p.height, b, e, p.halo)  # the gather
     buf.barrier()
-    return buf.frame if p.rank == 0 else None
+    return buf.frames[turn] if p.rank == 0 else None

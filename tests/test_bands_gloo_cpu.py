@@ -92,7 +92,7 @@ def single_process_frame(scene_file, width, height, rpp):
     (3, "DiffusionCurvePack/lady_bug.xml", 70, "blur, 3 ranks, ragged last strip"),
     (2, "DiffusionCurvePack/face.xml", 40, "blur reach deeper than a band"),
     (2, "arch.xml", 37, "no blur: gather of packed strips, uneven strip counts"),
-    (3, "arch.xml", 16, "fewer strips than ranks"),
+    (3, "arch.xml", 2 * rd.STRIP, "fewer strips than ranks"),
 ])
 def test_strips_reassemble_bit_exactly(world, scene_file, height, case, tmp_path):
     po.build()
@@ -109,16 +109,20 @@ def test_strips_reassemble_bit_exactly(world, scene_file, height, case, tmp_path
 def test_strip_plan_arithmetic():
     assert [rd.row_band(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert rd.halo_rows(0.0) == 0 and rd.halo_rows(1.5) == 5 and rd.halo_rows(16) == 48
+    S = rd.STRIP
     p = rd.StripPlan(1080, 1920, 8, 3, 0)
-    assert p.n_strips == 68 and p.packed_rows == 9 * 16 and p.local_strips == 9
-    assert rd.StripPlan(1080, 1920, 8, 4, 0).local_strips == 8
+    n = -(-1080 // S)  # strips
+    assert p.n_strips == n and p.packed_rows == -(-n // 8) * S and p.local_strips == len(range(3, n, 8))
+    assert rd.StripPlan(1080, 1920, 8, 7, 0).local_strips == len(range(7, n, 8))
     idx = p.source_index()
-    assert idx[0] == 0 and idx[16] == p.packed_rows and idx[8 * 16] == 16 and idx[1079] == 3 * p.packed_rows + 8 * 16 + 7
+    last = (1079 // S)
+    assert idx[0] == 0 and idx[S] == p.packed_rows and idx[8 * S] == S
+    assert idx[1079] == (last % 8) * p.packed_rows + (last // 8) * S + 1079 % S
     assert len(set(idx.tolist())) == 1080
     q = rd.StripPlan(100, 8, 3, 1, 5)
     bi = q.band_index()
     assert bi[0] == 0 and bi[34] == q.max_band_rows and bi[99] == 2 * q.max_band_rows + 32
-    assert rd.StripPlan(16, 8, 3, 2, 0).local_strips == 0
+    assert rd.StripPlan(2 * S, 8, 3, 2, 0).local_strips == 0
 
 
 def test_oracle_strips_equal_rows_of_the_full_frame():
@@ -126,6 +130,9 @@ def test_oracle_strips_equal_rows_of_the_full_frame():
     scene = po.ingest_xml(os.path.join(XML, "arch.xml"), True)
     full, _, _ = oracle.render(scene, po.make_params(20, 50, 8, zoom_factor=10.0))
     p = po.make_params(20, 50, 8, zoom_factor=10.0, strip_stride=2, strip_offset=1)
-    img, _ = render_packed(oracle, scene, p, 32)
-    assert np.array_equal(img[:16].view(np.uint32), full[16:32].view(np.uint32))
-    assert np.array_equal(img[16:18].view(np.uint32), full[48:50].view(np.uint32))
+    S = rd.STRIP
+    mine = [t for t in range(-(-50 // S)) if t % 2 == 1]  # strips of rank 1 of 2
+    img, _ = render_packed(oracle, scene, p, len(mine) * S)
+    for k, t in enumerate(mine):
+        rows = min(S, 50 - t * S)
+        assert np.array_equal(img[k * S:k * S + rows].view(np.uint32), full[t * S:t * S + rows].view(np.uint32))

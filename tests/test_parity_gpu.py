@@ -125,7 +125,7 @@ def test_row_bands_concatenate_bit_exactly(xml_dir, api):
 
 
 def test_interleaved_strips_reassemble_bit_exactly(xml_dir, api):
-    """The multi-GPU split (16-row strips dealt round-robin) emulated on one GPU: every rank's packed
+    """The multi-GPU split (8-row strips dealt round-robin) emulated on one GPU: every rank's packed
     strips, put back in order with distributed.StripPlan.source_index, equal the one-call frame."""
     import torch
 
