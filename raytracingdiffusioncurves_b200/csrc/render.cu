@@ -32,7 +32,8 @@ constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
-constexpr size_t kSmemSceneLimit = 40 * 1024;  // stage nodes + runs in shared memory below this
+constexpr size_t kSmemSceneLimit = 56 * 1024;  // stage nodes + runs in shared memory below this (4 blocks per SM still fit;
+                                               // measured: 40 -> 56 KB buys 4-7 % on the scenes it adds, 72 KB loses 8 % on the next ones)
 constexpr int kRunVec = sizeof(RunRecord) / 16;
 // local run table (scenes too large for the whole-scene table): per warp, the runs around the tile
 #ifndef RDC_LOCAL_WORDS
@@ -1169,7 +1170,9 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.row_skew = a.strip_stride > 1 ? 0u : p.row_begin % kWarpTileH;  // strips: give row_begin as a multiple of 4 for split-independent bits
   a.work = s->work_counters;
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
-  const bool smem = scene_bytes <= kSmemSceneLimit;
+  size_t smem_limit = kSmemSceneLimit;
+  if (const char* env = getenv("RDC_B200_SMEM_LIMIT")) smem_limit = (size_t)atol(env);  // tuning experiments only
+  const bool smem = scene_bytes <= smem_limit;
   const bool portals = s->info.has_portals != 0;
   // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
   const bool masks_ok = (float)n_iter == p.number_of_rays_per_pixel && n_iter >= 8 && !a.brute;
@@ -1235,10 +1238,13 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
   }
   // Units per tile. It must not depend on how the frame is divided among GPUs (the summation order is part of
-  // the result), so it is a function of the full frame only: as many as kMaxSplit while each unit keeps at
-  // least 16 rays and the partial sums of the whole frame fit 2 GiB.
+  // the result), so it is a function of the full frame only: enough for about 200 k units in the frame (40 per
+  // warp of one GPU; every unit pays for its run table, and at 3840x2160 one unit per tile measured 8 % faster
+  // than four), at most kMaxSplit, while each unit keeps at least 16 rays and the partial sums fit 2 GiB.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
-  uint32_t split = kMaxSplit;
+  const uint64_t frame_tiles = (uint64_t)tiles_x * ((p.image_height + kWarpTileH - 1) / kWarpTileH);
+  uint32_t split = 1;
+  while (split < (uint32_t)kMaxSplit && frame_tiles * split < 200000ull) split <<= 1;
   if (const char* env = getenv("RDC_B200_SPLIT")) {  // tuning experiments only
     int v = atoi(env);
     if (v == 1 || v == 2 || v == 4) split = (uint32_t)v;
