@@ -57,6 +57,10 @@ struct __align__(16) WarpLocal {
   uint32_t cand_key[kGatherCap];  // ... and their sort keys: distance bits with the position in the low byte
   uint32_t ring[kRingWords];      // query: nodes pending; ray loop: queue of deferred rays {lane << 16 | ray, bound}
   // (copying the slots' run records in here as well was measured: 10-15 % slower — fewer resident blocks)
+  // per-lane state that is only touched once per 32 iterations or per batch of deferred rays: kept out of registers
+  int first[kLocalWords][32], span[kLocalWords][32];  // ray-index interval of the slots the lane looks after
+  float deferred[5][32];                              // running sums of the lane's deferred samples: w, r*w, g*w, b*w, blur*w
+  int root_first, root_span;                          // the rays of the tile that can reach the scene at all
 };
 
 struct RenderArgs {
@@ -806,6 +810,10 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         if (!complete && !angular_interval(a.sc.root_box, ox0, ox1, oy0, oy1, n, first_root, span_root)) {
           first_root = 0; span_root = n - 1;
         }
+        if (lane == 0) {
+          wl->root_first = first_root;
+          wl->root_span = span_root;
+        }
       }
       constexpr int W = LOCAL ? kLocalWords : kTableWords;  // lane L looks after slots L, L+32, ...
       int first[W], span[W];                                  // span -1: never, n-1: always
@@ -816,12 +824,19 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
             !angular_interval(LOCAL ? wl->box[lane + 32 * k] : ac.run_box[lane + 32 * k], ox0, ox1, oy0, oy1, n, first[k], span[k])) {
           first[k] = 0; span[k] = n - 1;
         }
+        if (LOCAL) {
+          wl->first[k][lane] = first[k];
+          wl->span[k][lane] = span[k];
+        }
       }
       int last_slot = -1;       // the slot this lane's previous ray hit
       uint32_t queued = 0;      // deferred rays waiting in wl->ring
       // Deferred samples are summed apart from the direct ones and added at the end of the unit: when a batch
       // leaves depends on the other pixels of the tile (a band may cut some off), the two sums do not.
-      float dr = 0.0f, dg = 0.0f, db = 0.0f, dw = 0.0f, dblur = 0.0f;
+      if (LOCAL) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) wl->deferred[c][lane] = 0.0f;  // only ever touched by this lane: no barrier
+      }
 
       // Up to 32 deferred rays, one per lane: regenerate the ray (owner's pixel, ray index), closest chord by the
       // tree under the known bound, shade; then the owners add the samples in queue order.
@@ -861,6 +876,11 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           const Sample s = trace_from<SMEM, PORTALS, STATS>(a, ac, h, ox, oy, dx, dy, cnt);
           pw = s.w; pr = s.r * s.w; pg = s.g * s.w; pb = s.b * s.w; pblur = s.blur * s.w;
         }
+        // the running sums of the lane's deferred samples live in shared memory between batches (registers are
+        // scarce in the ray loop); inside a batch they are continued in registers, one entry after the other in
+        // queue order — where a batch ends must not matter to the bits
+        float dw = wl->deferred[0][lane], dr = wl->deferred[1][lane], dg = wl->deferred[2][lane];
+        float db = wl->deferred[3][lane], dblur = wl->deferred[4][lane];
 #pragma unroll 1
         for (uint32_t k = 0; k < batch; ++k) {
           const uint32_t o = __shfl_sync(0xFFFFFFFFu, owner, k);
@@ -873,6 +893,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
             dblur += bl;
           }
         }
+        wl->deferred[0][lane] = dw; wl->deferred[1][lane] = dr; wl->deferred[2][lane] = dg;
+        wl->deferred[3][lane] = db; wl->deferred[4][lane] = dblur;
       };
 
       // Which of this unit's rays (i = q + j*split) fall into the interval of the runs in slots L / L+32: one
@@ -887,11 +909,12 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         uint32_t mine = 0u;
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-          it[k] = iteration_mask(first[k], span[k], (int)q, shift, cb0, here, n);
+          it[k] = LOCAL ? iteration_mask(wl->first[k][lane], wl->span[k][lane], (int)q, shift, cb0, here, n)
+                        : iteration_mask(first[k], span[k], (int)q, shift, cb0, here, n);
           mine |= it[k];
         }
         any = __reduce_or_sync(0xFFFFFFFFu, mine);
-        if (LOCAL) any |= iteration_mask(first_root, span_root, (int)q, shift, cb0, here, n);
+        if (LOCAL) any |= iteration_mask(wl->root_first, wl->root_span, (int)q, shift, cb0, here, n);
         if (a.hit_ids && valid) {  // parity runs record every ray: mark the ones no run can reach
           uint32_t none = ~any & (here == 32 ? 0xFFFFFFFFu : (1u << here) - 1u);
           while (none) {
@@ -965,9 +988,11 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         }
       }
       if (LOCAL) {
-        weight_total += dw;
-        cr += dr; cg += dg; cb += db;
-        blur += dblur;
+        weight_total += wl->deferred[0][lane];
+        cr += wl->deferred[1][lane];
+        cg += wl->deferred[2][lane];
+        cb += wl->deferred[3][lane];
+        blur += wl->deferred[4][lane];
       }
     } else if (valid) {
       // Ray indices that can reach the scene: [lo0,hi0] and (when the angular range wraps) [lo1,hi1],
