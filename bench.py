@@ -304,11 +304,11 @@ def main():
     # ---- value: device-timed, inputs resident, L2 flushed between steps ----------------------------
     for s in range(args.warmup):
         frame_step(s)
-    barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.start()  # (NVML start-up takes milliseconds and differs from rank to rank: keep it in front of the barrier)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()  # all ranks enter the timed region together: a rank that came early would count its wait for the others
     wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.zero_()  # evict L2 between timed iterations (untimed)
