@@ -45,9 +45,9 @@ XML_DIR = os.path.join(ROOT, "tests", "golden", "xmls")
 F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
 
 # From the committed `ncu --set full` capture of k_render on the headline workload
-# (profiles/r01_k_render_v7_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
+# (profiles/r01c_k_render_arch_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
 NCU_CAPTURE = {
-    "arch_1080p_128rpp": {"dram_bytes": 3.698176e6 + 156.869632e6, "issue_active": 0.8236, "source": "profiles/r01b_k_render_arch_ncu_summary.txt"},
+    "arch_1080p_128rpp": {"dram_bytes": 3.639296e6 + 155.037184e6, "issue_active": 0.8130, "source": "profiles/r01c_k_render_arch_ncu_summary.txt"},
 }
 
 
