@@ -47,7 +47,9 @@ F_GEN, F_NODE, F_SEG, F_SHADE, F_ACC = 40.0, 30.0, 20.0, 100.0, 10.0
 # From the committed `ncu --set full` capture of k_render on the headline workload
 # (profiles/r01c_k_render_arch_ncu_summary.txt): DRAM bytes per launch and issue-slot utilisation.
 NCU_CAPTURE = {
-    "arch_1080p_128rpp": {"dram_bytes": 3.639296e6 + 155.037184e6, "issue_active": 0.8130, "source": "profiles/r01c_k_render_arch_ncu_summary.txt"},
+    # DRAM bytes: ncu pass with the partial sums' lines discarded after use (the shipped default), profiles/r01c_discard_partials.log;
+    # before that the same launch wrote 155 MB (profiles/r01c_k_render_arch_ncu_summary.txt, which also holds the issue-slot figure)
+    "arch_1080p_128rpp": {"dram_bytes": 3.64e6 + 30.32e6, "issue_active": 0.8130, "source": "profiles/r01c_discard_partials.log, profiles/r01c_k_render_arch_ncu_summary.txt"},
 }
 
 
@@ -471,8 +473,8 @@ def main():
                         "deferred_to_tree": deferred / band_rays, "table_query_nodes": gathered / band_rays},
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
-                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; measured DRAM traffic is ~4x that "
-                            "because the partial sums of split work units are written back (see DESIGN.md 3.1)"},
+                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; the partial sums of split work "
+                            "units stay in L2 (their lines are discarded once added up, see DESIGN.md 3.1)"},
         }
 
     cpu_baseline = None

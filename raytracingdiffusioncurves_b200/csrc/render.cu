@@ -88,6 +88,7 @@ struct RenderArgs {
   int orzan, use_aa, max_depth, brute, cull;
   float local_r0;  // local table: first radius tried around a tile
   // rdc_render_to_frames: finished pixels go to their place in up to RDC_MAX_FRAME_TARGETS FULL frames (peer memory)
+  int discard_partials;  // drop the partial sums' cache lines once they have been added up (they never reach HBM)
   uint32_t n_targets;
   float4* target_image[RDC_MAX_FRAME_TARGETS];
   float* target_blur[RDC_MAX_FRAME_TARGETS];
@@ -1054,6 +1055,22 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
             blur += __ldcg(a.part_blur + k * part_stride + local_pixel);
           }
         }
+        // The partial sums are dead now, but their lines would still be written back to HBM when L2 evicts them —
+        // 4x the frame's algorithmic bytes (profiles/r01c_k_render_arch_ncu_summary.txt: 155 MB written for a 41 MB
+        // frame). A tile row's eight float4 are exactly one aligned 128-byte line when the row lies inside the image:
+        // tell L2 to drop it. Measured (profiles/r01c_discard_partials.log): 155 -> 30 MB written, frame time unchanged.
+        if (a.discard_partials) {
+          __syncwarp();  // every lane of the row has its partial sums
+          const uint32_t row_x0 = (tile % tiles_x) * kWarpTileW;
+          if ((lane & 7u) == 0u && valid && row_x0 + kWarpTileW <= a.width) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < a.split; ++k) {
+              const float4* line = a.part_rgbw + k * part_stride + local_pixel;
+              if ((reinterpret_cast<uintptr_t>(line) & 127u) == 0u)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+            }
+          }
+        }
       }
     }
     if (finish && valid) {
@@ -1158,6 +1175,7 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.sc = s->dev;
   a.image = image;
   a.blur_map = blur_map;
+  a.discard_partials = getenv("RDC_B200_KEEP_PARTIALS") == nullptr;  // the variable only exists to measure the difference
   a.n_targets = n_targets;
   for (uint32_t t = 0; t < n_targets; ++t) {
     a.target_image[t] = reinterpret_cast<float4*>(target_images[t]);
