@@ -188,6 +188,9 @@ int rdc_image_to_rgba8(const float* image, int width, int height, int flip, uint
 /* binary PPM (P6) and PNG (RGBA, uncompressed deflate) writers for headless runs */
 int rdc_write_ppm(const char* path, const uint8_t* rgba, int width, int height);
 int rdc_write_png(const char* path, const uint8_t* rgba, int width, int height);
+/* baseline JPEG (JFIF, YCbCr 4:4:4), the format of the reference's screenshot: stbi_write_jpg(name, W, H, 4, rgba, W*4)
+ * at glfw_events.cpp:94 — alpha ignored, and its out-of-range quality argument ends up as 100. quality 1..100. */
+int rdc_write_jpg(const char* path, const uint8_t* rgba, int width, int height, int quality);
 
 /* ---- the steps either side of the path in the frame loop ---- */
 /* scroll_callback (glfw_events.cpp:105-112): zoom_factor *= 1.5^-yoffset */

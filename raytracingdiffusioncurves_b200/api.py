@@ -108,6 +108,7 @@ PROTOTYPES = {
     "rdc_image_to_rgba8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rdc_write_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "rdc_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "rdc_write_jpg": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rdc_view_scroll": (None, [C.POINTER(FrameParams), C.c_double]),
     "rdc_view_drag": (None, [C.POINTER(FrameParams), C.c_double, C.c_double]),
     "rdc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),

@@ -32,7 +32,7 @@
   } while (0)
 
 static void usage_options() {
-  std::cout << "options: --width W --height H --frames N --out file.ppm|file.png --save-cache scene.rdc --zoom Z --offset-x X --offset-y Y\n"
+  std::cout << "options: --width W --height H --frames N --out file.ppm|file.png|file.jpg --save-cache scene.rdc --zoom Z --offset-x X --offset-y Y\n"
                "         --seed S --max-depth D --tolerance T --curve-width R --endcap-size E --weight-degree G\n"
                "         --native (not an Orzan save) --no-blur --no-aa --denoiser (ignored) --brute-force --device I\n";
 }
@@ -165,8 +165,14 @@ int main(int argc, char* argv[]) {
     // Orzan saves are rendered bottom-up (DeviceCode.cu:104-105) and shown with glDrawPixels; the
     // screenshot flips them into a top-down file (glfw_events.cpp:92). Same rule here.
     CALL_CHECK(rdc_image_to_rgba8(host_image, width, height, ingest.use_diffusion_curve_save ? 1 : 0, rgba.data()));
-    const bool png = out_path.size() > 4 && out_path.compare(out_path.size() - 4, 4, ".png") == 0;
-    CALL_CHECK(png ? rdc_write_png(out_path.c_str(), rgba.data(), width, height) : rdc_write_ppm(out_path.c_str(), rgba.data(), width, height));
+    auto ends_with = [&](const char* ext) {
+      const size_t n = std::strlen(ext);
+      return out_path.size() > n && out_path.compare(out_path.size() - n, n, ext) == 0;
+    };
+    if (ends_with(".png")) CALL_CHECK(rdc_write_png(out_path.c_str(), rgba.data(), width, height));
+    else if (ends_with(".jpg") || ends_with(".jpeg"))  // the screenshot's format; its quality argument ends up as 100
+      CALL_CHECK(rdc_write_jpg(out_path.c_str(), rgba.data(), width, height, 100));
+    else CALL_CHECK(rdc_write_ppm(out_path.c_str(), rgba.data(), width, height));
     std::cout << "Wrote " << out_path << std::endl;
   }
   cudaFreeHost(host_image);
