@@ -203,9 +203,9 @@ int rdc_xml_dump_file(const char* path, char** out_text) {
     return RDC_E_INVALID;
   }
   return guarded(RDC_E_PARSE, [&]() {
-    auto root = rdc::xml_parse_file(path);
+    auto doc = rdc::xml_parse_file(path);
     std::string s;
-    rdc::xml_dump(*root, 0, s);
+    rdc::xml_dump(*doc->root, 0, s);
     char* buf = (char*)std::malloc(s.size() + 1);
     if (!buf) throw std::bad_alloc();
     std::memcpy(buf, s.c_str(), s.size() + 1);

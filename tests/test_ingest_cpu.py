@@ -141,3 +141,46 @@ def test_scene_cache_round_trip(xml_dir, tmp_path):
     with pytest.raises(api.RdcError) as e:
         api.HostScene.from_cache(str(tmp_path / "missing.rdc"))
     assert e.value.code == -3
+
+
+def test_xml_tree_edge_cases(tmp_path):
+    """The in-place parser: entities decoded where they stand, both quote styles, empty elements, everything that is
+    not an element skipped (the nodes rapidxml's parse<0> does not create), errors with a line number."""
+    doc = tmp_path / "edge.xml"
+    doc.write_bytes(
+        b"\xef\xbb\xbf<?xml version='1.0'?>\n<!DOCTYPE a [ <!ENTITY x 'y'> ]>\n<!-- c <b/> -->\n"
+        b"<a k=\"1 &amp; 2\" q='say &quot;hi&quot; &#65;&#x42;&#xe9; &unknown; &lt;&gt;&apos;'>text <![CDATA[ <z/> ]]>\n"
+        b" <b/><b x = \"2\" />\n <c>\n  <d name=\"it's\"></d>\n </c>\n</a>\n<trailing/>\n")
+    assert api.xml_dump(str(doc)) == (
+        "a k=1 & 2 q=say \"hi\" ABé &unknown; <>'\n"
+        " b\n"
+        " b x=2\n"
+        " c\n"
+        "  d name=it's\n")
+    for text, what in (("<a><b></a>", "closes"), ("<a", "unterminated"), ("<a x=1/>", "quoted"), ("<a x='1/>", "unterminated"),
+                       ("", "no root"), ("<a>\n\n<b>\n</b>", "line 4"), ("<!-- never closed <a/>", "unterminated"),
+                       ("<a>" * 600 + "</a>" * 600, "nested")):
+        bad = tmp_path / "bad.xml"
+        bad.write_text(text)
+        with pytest.raises(api.RdcError) as e:
+            api.xml_dump(str(bad))
+        assert e.value.code == -2 and what in str(e.value), (text[:20], str(e.value))
+
+
+def test_numbers_are_read_like_atof(tmp_path):
+    """Attribute values go through a fast exact parser with atof as the fallback: same floats either way."""
+    def scene(xs):
+        pts = "".join(f"<control_point x='{x}' y='{i}'/>" for i, x in enumerate(xs))
+        return (f"<curve_set image_width='0' image_height='0'><curve><control_points_set>{pts}</control_points_set>"
+                "<left_colors_set><left_color R='1' G='2' B='3' globalID='0'/><left_color R='1' G='2' B='3' globalID='10'/></left_colors_set>"
+                "<right_colors_set><right_color R='1' G='2' B='3' globalID='0'/><right_color R='1' G='2' B='3' globalID='10'/></right_colors_set>"
+                "<blur_points_set><best_scale value=' 1.5' globalID='0'/><best_scale value='+2.25x' globalID='1e1'/></blur_points_set>"
+                "</curve></curve_set>")
+    xs = ["0.1", " 7.25", "+3", "1e-3junk"]
+    s = api.HostScene.from_xml_text(scene(xs).encode(), api.default_ingest_options(use_diffusion_curve_save=0)).to_numpy()
+    want = np.array([np.float32(float(v)) for v in ("0.1", "7.25", "3", "1e-3")], np.float32)
+    # Bezier (b0..b3) -> B-spline control points; b0 = (V0 + 4 V1 + V2)/6 recovers the first value
+    v = s["vertices"][:4, 0].astype(np.float64)
+    bezier = [(v[0] + 4 * v[1] + v[2]) / 6, (2 * v[1] + v[2]) / 3, (v[1] + 2 * v[2]) / 3, (v[1] + 4 * v[2] + v[3]) / 6]
+    np.testing.assert_allclose(bezier, want, atol=2e-5)
+    assert s["blur"][:2].tolist() == [1.5, 2.25] and s["blur_u"][:2].tolist() == [0.0, 1.0]
