@@ -1,7 +1,8 @@
-"""N > 1 host logic on CPU: world_size 2 and 3 over gloo. The band plan, the blur-halo exchange and the
-gather of raytracingdiffusioncurves_b200.distributed run for real; what renders and blurs a band is the
-CPU oracle (injected — the product module itself never touches oracle/). The assembled frame must equal the
-single-process frame bit for bit."""
+"""N > 1 host logic on CPU: world_size 2 and 3 over gloo. The strip plan, the exchange steps and the
+gather of raytracingdiffusioncurves_b200.distributed run for real — the collective form (render_frame) and the
+peer-memory form (render_frame_peer, with shared host memory standing in for NVLink peer memory); what renders
+and blurs is the CPU oracle (injected — the product module itself never touches oracle/). The assembled frame
+must equal the single-process frame bit for bit."""
 import os
 import socket
 
@@ -136,3 +137,93 @@ def test_oracle_strips_equal_rows_of_the_full_frame():
     for k, t in enumerate(mine):
         rows = min(S, 50 - t * S)
         assert np.array_equal(img[k * S:k * S + rows].view(np.uint32), full[t * S:t * S + rows].view(np.uint32))
+
+
+# ---- the peer-memory form (distributed.render_frame_peer) with shared host memory standing in for NVLink peer memory ----
+
+class SharedPeerBuffers:
+    """What distributed.PeerFrameBuffers is on GPUs: every rank can store into every rank's frame buffers. Here the
+    buffers are shared-memory CPU tensors and an 'address' is the tensor itself."""
+
+    def __init__(self, plan, images, sigmas, frames):
+        self.plan = plan
+        self.image_ptrs, self.sigma_ptrs, self.frame_ptrs = images, sigmas, frames  # [rank], [rank], [turn][rank]
+        self.full_image, self.full_sigma = images[plan.rank], sigmas[plan.rank]
+        self.frames = [frames[0][plan.rank], frames[1][plan.rank]]
+        self.scratch = None
+        self.turn = 0
+        self.barriers = 0
+
+    def barrier(self):
+        self.barriers += 1
+        dist.barrier()
+
+
+def peer_worker(rank, world, port, scene_file, width, height, rpp, halo, images, sigmas, frames, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle = po.Oracle("port")
+        scene = po.ingest_xml(os.path.join(XML, scene_file), True)
+        zoom = scene["image_height"] / height
+        plan = rd.StripPlan(height, width, world, rank, halo)
+        buf = SharedPeerBuffers(plan, images, sigmas, frames)
+        frame_no = [0]
+
+        def render_to(image_targets, sigma_targets, stride, offset):
+            p = po.make_params(width, height, rpp, zoom_factor=zoom, strip_stride=stride, strip_offset=offset, frame=frame_no[0])
+            img, sig = render_packed(oracle, scene, p, plan.packed_rows)
+            for k, t in enumerate(plan.strips_of(offset)):  # every finished row straight to its place in every target
+                rows = min(rd.STRIP, height - t * rd.STRIP)
+                for image, sigma in zip(image_targets, sigma_targets):
+                    image[t * rd.STRIP:t * rd.STRIP + rows].copy_(torch.from_numpy(img[k * rd.STRIP:k * rd.STRIP + rows]))
+                    sigma[t * rd.STRIP:t * rd.STRIP + rows].copy_(torch.from_numpy(sig[k * rd.STRIP:k * rd.STRIP + rows]))
+
+        def blur_rows(dest, source, sigma, scratch, rows, row_begin, row_end, halo_rows):
+            out = oracle.blur(source[:rows].numpy(), sigma[:rows].numpy(), threads=2)
+            dest[row_begin:row_end].copy_(torch.from_numpy(out[row_begin:row_end]))
+
+        hooks = []
+        got = []
+        for f in range(3):  # three frames: both frame buffers are used, one of them twice
+            frame_no[0] = f
+            frame = rd.render_frame_peer(buf, render_to, blur_rows, use_blur=True, before_barrier=lambda: hooks.append(f))
+            if rank == 0:
+                assert frame is frames[f % 2][0]
+                got.append(frame.numpy().copy())
+            else:
+                assert frame is None
+        assert hooks == [0, 1, 2] and buf.barriers == (6 if halo > 0 else 3)
+        if rank == 0:
+            np.save(out_path, np.stack(got))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,scene_file,height,case", [
+    (2, "DiffusionCurvePack/lady_bug.xml", 44, "blur: stores into every rank's frame, band blur into rank 0's"),
+    (3, "arch.xml", 37, "no blur: stores into rank 0's frame only"),
+])
+def test_peer_memory_form_reassembles_bit_exactly(world, scene_file, height, case, tmp_path):
+    po.build()
+    width, rpp = 36, 6
+    oracle = po.Oracle("port")
+    scene = po.ingest_xml(os.path.join(XML, scene_file), True)
+    sigma_bound = float(scene["blur"][: scene["n_blur"]].max())
+    halo = rd.halo_rows(sigma_bound)
+    shared = lambda *shape: torch.full(shape, float("nan"), dtype=torch.float32).share_memory_()  # noqa: E731
+    images = [shared(height, width, 4) for _ in range(world)]
+    sigmas = [shared(height, width) for _ in range(world)]
+    frames = [[shared(height, width, 4) for _ in range(world)] for _ in range(2)]
+    out = str(tmp_path / "frames.npy")
+    mp.spawn(peer_worker, args=(world, free_port(), scene_file, width, height, rpp, halo, images, sigmas, frames, out),
+             nprocs=world, join=True)
+    got = np.load(out)
+    for f in range(3):
+        p = po.make_params(width, height, rpp, zoom_factor=scene["image_height"] / height, frame=f)
+        img, sig, _ = oracle.render(scene, p)
+        want = oracle.blur(img, sig) if halo > 0 else img
+        assert np.array_equal(got[f][..., :3].view(np.uint32), want[..., :3].view(np.uint32)), (case, f)
+    assert not np.array_equal(got[0].view(np.uint32), got[1].view(np.uint32))  # the frame number keys the generator
