@@ -169,9 +169,19 @@ class PeerFrameBuffers:
         p = self.plan = plan
         group = group if group is not None else dist.group.WORLD
         f32 = dict(dtype=torch.float32, device=device)
-        self.full_image = symm.empty((p.height, p.width, 4), **f32)
-        self.full_sigma = symm.empty((p.height, p.width), **f32)
-        self.frames = [symm.empty((p.height, p.width, 4), **f32) for _ in range(2)]
+        # Allocation is local and may fail on one rank only; the rendezvous below is collective. Agree first, so
+        # that no rank waits in a rendezvous the others never enter.
+        error = None
+        try:
+            self.full_image = symm.empty((p.height, p.width, 4), **f32)
+            self.full_sigma = symm.empty((p.height, p.width), **f32)
+            self.frames = [symm.empty((p.height, p.width, 4), **f32) for _ in range(2)]
+        except Exception as exc:  # noqa: BLE001
+            error = exc
+        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError(f"symmetric memory could not be allocated on every rank ({error!r} here)")
         self.h_image = symm.rendezvous(self.full_image, group)
         self.h_sigma = symm.rendezvous(self.full_sigma, group)
         self.h_frames = [symm.rendezvous(f, group) for f in self.frames]
