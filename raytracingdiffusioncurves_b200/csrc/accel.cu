@@ -491,6 +491,13 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     BUILD_CUDA(cudaMemcpyAsync(h_base.data(), base, (nseg + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     BUILD_CUDA(cudaStreamSynchronize(stream));
     std::vector<uint4> hints(2 * (size_t)n_chords);
+#ifdef RDC_SHADE_RECORDS
+    // the table only pays while it stays in L2 next to everything else: 32 MB at most (250 k chords)
+    const bool with_records = (size_t)n_chords * 128 <= (32u << 20) && getenv("RDC_B200_NO_RECORDS") == nullptr;
+    std::vector<float4> records(with_records ? 8 * (size_t)n_chords : 0);
+    const float* scalar_v[3] = {a.blur, a.weight, a.weight_degree};
+    const float* colour_v[2] = {a.color_left, a.color_right};
+#endif
     for (uint32_t sg = 0; sg < nseg; ++sg) {
       const uint32_t c = a.curve_map[sg];
       const int K = (int)(h_base[sg + 1] - h_base[sg]);
@@ -511,9 +518,37 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
         }
         hints[2 * (size_t)(h_base[sg] + k)] = make_uint4(f[0], f[1], f[2], f[3]);
         hints[2 * (size_t)(h_base[sg] + k) + 1] = make_uint4(f[4], f[5], 0u, 0u);
+#ifdef RDC_SHADE_RECORDS
+        if (with_records) {
+          // the largest parameter a hit on this chord can have: s = 1 (rounding is monotone, so every hit lies in between)
+          const float cu_max = rdc_hit_u(k, K, 1.0f) + a.curve_index[sg];
+          uint32_t flags = 0;
+          for (int fam = 0; fam < 5; ++fam) {  // family `fam` is simple when the walk would not step even at cu_max
+            const uint32_t end = idx[fam][2 * c] + idx[fam][2 * c + 1];
+            if (!(f[fam] < end && us[fam][f[fam] + 1] < cu_max)) flags |= 1u << fam;
+          }
+          float4* rec = &records[8 * (size_t)(h_base[sg] + k)];
+          for (int sf = 0; sf < 3; ++sf) {  // blur, weight, exponent: families 2, 3, 4
+            const uint32_t j = f[2 + sf];
+            rec[sf] = make_float4(us[2 + sf][j], us[2 + sf][j + 1], scalar_v[sf][j], scalar_v[sf][j + 1]);
+          }
+          for (int side = 0; side < 2; ++side) {  // left, right colour: families 0, 1
+            const uint32_t j = f[side];
+            const float* v = colour_v[side];
+            rec[3 + 2 * side] = make_float4(v[3 * j], v[3 * j + 1], v[3 * j + 2], us[side][j]);
+            rec[4 + 2 * side] = make_float4(v[3 * (j + 1)], v[3 * (j + 1) + 1], v[3 * (j + 1) + 2], us[side][j + 1]);
+          }
+          uint4 meta = make_uint4(sg, a.curve_index[sg], (uint32_t)k | ((uint32_t)K << 16), (c & 0x07FFFFFFu) | (flags << 27));
+          if (K > 0xFFFF || c > 0x07FFFFFFu) meta.w &= 0x07FFFFFFu;  // does not fit the packing: never simple
+          std::memcpy(&rec[7], &meta, sizeof meta);
+        }
+#endif
       }
     }
     d.chord_walk = up.upload(hints.data(), hints.size());
+#ifdef RDC_SHADE_RECORDS
+    d.chord_records = with_records ? up.upload(records.data(), records.size()) : nullptr;
+#endif
     BUILD_CUDA(cudaStreamSynchronize(stream));  // `hints` leaves scope
     if (up.status) return fail(up.status);
   }

@@ -65,6 +65,13 @@ struct DevScene {
   const uint32_t* seg_chord_count; // [n_segments]   K
   const SegWalk* seg_walk;         // [n_segments]
   const uint4* chord_walk;         // [2*n_chords] per chord: walk start of left, right, blur, weight | degree, portal-left
+#ifdef RDC_SHADE_RECORDS
+  // Experiment (make variantd NAME=rec DEFS=-DRDC_SHADE_RECORDS; not in the shipped build): per chord, the two stops of
+  // every family its hits interpolate between — 8 x 16 bytes: blur, weight, exponent {u0,u1,v0,v1}; left colour
+  // {rgb0,u0} {rgb1,u1}; right colour likewise; {segment, ordinal, k | K << 16, curve | flags << 27}. flags 0x1F: every
+  // family stays inside one stop interval over the whole chord, and the record replaces the walks. nullptr: no table.
+  const float4* chord_records;
+#endif
   // acceleration structure: what rays touch
   const RunRecord* runs;           // [n_runs] Morton order
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K

@@ -362,6 +362,36 @@ __device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& a
   for (;;) {
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
     if (STATS) cnt.shaded++;
+#ifdef RDC_SHADE_RECORDS
+    // Experiment (see device_scene.h): one 128-byte record instead of run ids -> walk hints -> stop parameters -> stop
+    // values. Same operands, same operations, same bits as the walks below for a chord whose hits all interpolate
+    // between the same two stops of every family.
+    if (!PORTALS && sc.chord_records) {
+      const float4* rec = sc.chord_records + 8 * (size_t)h.id;
+      const float4 m4 = __ldg(rec + 7);
+      const uint32_t meta_w = __float_as_uint(m4.w);
+      if ((meta_w >> 27) == 0x1Fu) {
+        const uint32_t seg = __float_as_uint(m4.x), ordinal = __float_as_uint(m4.y), kk = __float_as_uint(m4.z);
+        const float u = rdc_hit_u((int)(kk & 0xFFFFu), (int)(kk >> 16), h.s);
+        const float cu = u + ordinal;
+        const float4 sb = __ldg(rec), sw = __ldg(rec + 1), sd = __ldg(rec + 2);
+        const float blur_here = rdc_lerp_stop(sb.z, sb.w, rdc_ratio(cu - sb.x, sb.y - sb.x));
+        const float wm = rdc_lerp_stop(sw.z, sw.w, rdc_ratio(cu - sw.x, sw.y - sw.x));
+        const float e = rdc_lerp_stop(sd.z, sd.w, rdc_ratio(cu - sd.x, sd.y - sd.x));
+        rdc_f2 v[4];
+        load_control_points(sc, seg, v);
+        const bool right = rdc_is_ray_right(u, dx, dy, v[0], v[1], v[2], v[3], a.orzan != 0);
+        const float4 c0 = __ldg(rec + (right ? 5 : 3)), c1 = __ldg(rec + (right ? 6 : 4));
+        const float ratio = rdc_ratio(cu - c0.w, c1.w - c0.w);
+        out.r = rdc_lerp_color(c0.x, c1.x, ratio);
+        out.g = rdc_lerp_color(c0.y, c1.y, ratio);
+        out.b = rdc_lerp_color(c0.z, c1.z, ratio);
+        out.blur = blur_here;
+        out.w = wm * rdc_weight_falloff(h.t, e);
+        return out;
+      }
+    }
+#endif
     const uint4 id = __ldg(sc.run_ids + h.leaf);  // first chord id, segment, k of the first chord, K
     const uint32_t seg = id.y;
     const float u = rdc_hit_u((int)id.z + h.j, (int)id.w, h.s);
