@@ -1,19 +1,23 @@
 // render.cu — per-frame ray generation, closest-chord traversal, shading, weighted normalisation.
 //
 // Replaces optixLaunch(...) of DeviceCode.cu's three programs (optixHello.cpp:1184):
-//   __raygen__rg      DeviceCode.cu:85-182   -> k_render's pixel loop
-//   __closesthit__ch  DeviceCode.cu:194-342  -> trace_ray (terminal :328-340, portal :220-320 as an
+//   __raygen__rg      DeviceCode.cu:85-182   -> k_render's pixel loop (gen_ray, accumulate)
+//   __closesthit__ch  DeviceCode.cu:194-342  -> trace_from (terminal :328-340, portal :220-320 as an
 //                                               iterative re-trace loop, shape of DeviceCodeIt.cu:151-170)
 //   __miss__ms        DeviceCode.cu:185-192  -> zero contribution
-//   RT-core traversal + built-in curve intersector (closed) -> closest_chord over the LBVH of accel.cu
+//   RT-core traversal + built-in curve intersector (closed) -> closest chord by one of three routes:
+//       table_closest over a whole-scene run table (at most 64 runs), table_closest over a per-tile table of
+//       the nearest runs with the far rays deferred to the tree (1024 runs or more, gather_local), or
+//       closest_chord over the LBVH of accel.cu (everything else, portal continuations, deferred rays)
 // Compiled with -fmad=false: plain expressions keep the reference's operation order and rounding; fused
 // operations appear only through rdc_fma (rdc_math.h).
 //
 // Work that cannot change the result is skipped, never approximated:
 //   * a ray whose angular stratum cannot reach the scene's box from anywhere inside its pixel is a miss
 //     (contributes zero, DeviceCode.cu:185-192) and is not generated at all (pixel_cull);
-//   * tree culling only uses conservative box tests; the accepted hit is the lexicographic minimum of
-//     (t, chord id) over all chords, the same rule the brute-force oracle applies.
+//   * tree and table culling only use conservative tests (padded boxes, widened angular intervals, shrunk
+//     distances); the accepted hit is the lexicographic minimum of (t, chord id) over all chords, the same
+//     rule the brute-force oracle applies.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
