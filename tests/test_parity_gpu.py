@@ -384,6 +384,44 @@ def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path, monkeypa
         assert np.array_equal(bits(np.concatenate([q["image"] for q in parts])), bits(plain["image"]))
 
 
+@pytest.mark.skipif(os.environ.get("RDC_TEST_UNVERIFIED") != "1",
+                    reason="written without a GPU at hand (round 1 budget spent): enable with RDC_TEST_UNVERIFIED=1, then drop the mark")
+def test_local_run_table_with_portals(api, port_oracle, tmp_path, monkeypatch):
+    """the local-table kernel on a scene that has `connects` curves — primary hits settled by
+    the table continue through portals on the tree; deferred rays do the same."""
+    import re
+
+    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")
+    xml = api.synth_xml(1500, 512, 512).decode()
+    count = [0]
+
+    def connect(m):  # curves 10k <-> 10k+1 become a portal pair (every synthetic curve has one segment)
+        c = count[0]
+        count[0] += 1
+        if c % 10 == 0:
+            return f'<curve connects="{c + 1}" '
+        if c % 10 == 1:
+            return f'<curve connects="{c - 1}" '
+        return m.group(0)
+
+    xml = re.sub(r"<curve ", connect, xml)
+    f = tmp_path / "synth_portals.xml"
+    f.write_text(xml)
+    scene = po.ingest_xml(str(f), True)
+    assert (scene["curve_connect"] >= 0).sum() == 300
+    r = GpuRenderer(str(f))
+    for depth in (0, 2, 31):
+        p = po.make_params(64, 48, 16, zoom_factor=1.0, offset_x=20.0, offset_y=-30.0, max_trace_depth=depth)
+        oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
+        out = r.render(product_params(api, p), want_hits=True, want_stats=True)
+        assert np.array_equal(out["hits"], ohits)
+        compare_images(out["image"], oimg, RGB_TOL)
+        assert out["stats"][5] > 0, "the local run table was not used"
+        plain = r.render(product_params(api, p), want_hits=True)
+        assert np.array_equal(plain["hits"], ohits)
+        compare_images(plain["image"], oimg, RGB_TOL)
+
+
 def test_accumulate_is_a_running_mean(api):
     import torch
 
