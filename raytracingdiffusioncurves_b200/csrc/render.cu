@@ -370,11 +370,18 @@ __device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& a
     // Shading records (device_scene.h): one 128-byte record instead of run ids -> walk hints -> stop parameters -> stop
     // values. Same operands, same operations, same bits as the walks below for a chord whose hits all interpolate
     // between the same two stops of every family (1.879 -> 1.762 ms on the headline frame).
-    if (!PORTALS && sc.chord_records) {
+#ifdef RDC_SHADE_RECORDS_PORTALS
+    // Not in the shipped build (never run on a GPU): terminal hits of scenes that have portals take the record, too —
+    // the record names the curve, and a curve that connects nowhere ends the ray.
+    constexpr bool kRecordsWithPortals = true;
+#else
+    constexpr bool kRecordsWithPortals = false;
+#endif
+    if ((!PORTALS || kRecordsWithPortals) && sc.chord_records) {
       const float4* rec = sc.chord_records + 8 * (size_t)h.id;
       const float4 m4 = __ldg(rec + 7);
       const uint32_t meta_w = __float_as_uint(m4.w);
-      if ((meta_w >> 27) == 0x1Fu) {
+      if ((meta_w >> 27) == 0x1Fu && (!PORTALS || __ldg(sc.curve_connect + (meta_w & 0x07FFFFFFu)) < 0)) {
         const uint32_t seg = __float_as_uint(m4.x), ordinal = __float_as_uint(m4.y), kk = __float_as_uint(m4.z);
         const float u = rdc_hit_u((int)(kk & 0xFFFFu), (int)(kk >> 16), h.s);
         const float cu = u + ordinal;
@@ -392,6 +399,11 @@ __device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& a
         out.b = rdc_lerp_color(c0.z, c1.z, ratio);
         out.blur = blur_here;
         out.w = wm * rdc_weight_falloff(h.t, e);
+        if (PORTALS && depth > 0) {  // behind portals: the carried filter, blur product and 1/w sum (as below)
+          out.r = Fr * out.r; out.g = Fg * out.g; out.b = Fb * out.b;
+          out.blur = Bp * blur_here;
+          out.w = 1.0f / (1.0f / out.w + S);
+        }
         return out;
       }
     }
