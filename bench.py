@@ -9,10 +9,13 @@ A "step" is one frame of the hot path: ray generation + closest-hit traversal + 
 xmls/arch.xml at 1920x1080, 128 rays per pixel, Orzan flag / blur / per-ray jitter as shipped, denoiser
 off. The metric is Grays/s = primary rays per second (W*H*rpp / t_frame / 1e9), whole job.
 
-N > 1: the image is dealt out in 8-row strips, round-robin over the ranks (scene + tree replicated); the
-strips are gathered to rank 0 over NVLink (NCCL); scenes with blur all-gather the rendered frame and every
-rank blurs one contiguous band before the gather (raytracingdiffusioncurves_b200/distributed.py). Total
-work is fixed as N grows ("strong" scaling); every exchange is inside the timed region.
+N > 1: the image is dealt out in 8-row strips, round-robin over the ranks (scene + tree replicated). The
+frame reaches rank 0 through peer memory: the render kernel of every rank stores its finished pixels straight
+into rank 0's frame over NVLink (rdc_render_to_frames on symmetric memory), then one barrier; scenes with blur
+store the rendered frame into every rank's buffer, every rank blurs one contiguous band and the blur stores it
+into rank 0's frame (raytracingdiffusioncurves_b200/distributed.py: render_frame_peer). Where symmetric memory
+cannot be set up, or with RDC_BENCH_NCCL=1, the same split runs on NCCL gather / all-gather (render_frame).
+Total work is fixed as N grows ("strong" scaling); every exchange is inside the timed region.
 
 Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
 """
