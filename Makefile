@@ -8,8 +8,9 @@ CSRC      := $(PKG)/csrc
 BUILD     := build
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false / -ffp-contract=off: see the arithmetic contract at the top of csrc/rdc_math.h
-# -DRDC_SHADE_RECORDS: per-chord shading records (device_scene.h); build without it to measure the difference
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall -Iinclude -DRDC_SHADE_RECORDS
+# per-chord shading records (device_scene.h); `make variantd NAME=norec RECORDS=` builds without them to measure the difference
+RECORDS   ?= -DRDC_SHADE_RECORDS
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall -Iinclude $(RECORDS)
 CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Iinclude
 
 LIB       := $(PKG)/librdc_b200.so
