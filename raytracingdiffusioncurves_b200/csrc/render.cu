@@ -30,8 +30,8 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a tile: 8x4 pixels, one lane per pixel, all lanes on the same ray index
-constexpr int kMaxSplit = 4;
-constexpr uint32_t kTableRuns = 64;             // scenes with at most this many runs use the per-tile run table                    // a tile's rays may be dealt to up to 4 work units (rdc_scene::split)
+constexpr int kMaxSplit = 4;                    // a tile's rays may be dealt to up to 4 work units (RenderArgs::split)
+constexpr uint32_t kTableRuns = 64;             // scenes with at most this many runs use the whole-scene run table
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
 constexpr int kStack = 64;
