@@ -6,7 +6,14 @@
  * reference's optixHello/ directory). Plain pointers and sizes only; every entry point that can fail
  * returns int (0 = ok, >0 = cudaError_t, <0 = RDC_E_*), never throws, and records a message readable
  * through rdc_last_error_string(). Entry points that take a stream only enqueue work on it (no hidden
- * synchronisation) unless their comment says otherwise.
+ * synchronisation) unless their comment says otherwise. Nothing in the library reads the environment: every
+ * switch is a field of one of the structs below.
+ *
+ * Threading (optixHello.cpp runs one host thread and one stream): a handle (rdc_scene, rdc_group) may be used from
+ * one host thread at a time. Device work of one rdc_scene is serialised by the library — a launch on the handle
+ * first waits (stream-ordered, no host wait) for the handle's previous launch, whatever stream that was given —
+ * because every launch shares the handle's work counters and scratch. Use one handle per device and per
+ * concurrently rendered frame.
  */
 #ifndef RDC_B200_H
 #define RDC_B200_H
@@ -77,6 +84,8 @@ typedef struct rdc_accel_options {
   float flatness_tolerance;  /* max |curve - chord| in XML pixels; chords per segment follow from it */
   int max_chords_per_segment;
   int run_length;            /* chords per tree leaf, 1..8; 0 = choose from the scene's density        */
+  int shading_records;       /* per-chord 128-byte shading records: 0 = library default (built when the
+                                table fits 32 MB), -1 = never (shading walks the stop lists)            */
 } rdc_accel_options;
 
 typedef struct rdc_scene rdc_scene; /* opaque: device-resident SoA scene + chords + LBVH, one per device */
@@ -105,6 +114,11 @@ void rdc_scene_destroy(rdc_scene* scene);
 #define RDC_STRIP_ROWS 8
 #define RDC_TRAVERSAL_LBVH 0
 #define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
+/* how primary rays find their closest chord (rdc_frame_params::route); every route gives the same bits */
+#define RDC_ROUTE_AUTO 0        /* whole-scene run table up to 64 runs, per-tile local run table for large scenes
+                                   seen closely enough, the tree otherwise                                    */
+#define RDC_ROUTE_TREE 1        /* always the LBVH                                                            */
+#define RDC_ROUTE_LOCAL_TABLE 2 /* per-tile local run table whenever the scene has more than 64 runs          */
 
 typedef struct rdc_frame_params {
   uint32_t image_width, image_height;   /* output size (params.h:48-49)                               */
@@ -132,9 +146,21 @@ typedef struct rdc_frame_params {
                                            table deferred to the tree, nodes visited by the table queries.
                                            Selects a slower counting build of the kernel; feeds the
                                            roofline's work-per-ray figure                */
+  int route;                            /* RDC_ROUTE_*; 0 = automatic                                    */
+  uint32_t units_per_tile;              /* work units a tile's rays are dealt to: 0 = automatic (a function of
+                                           the full frame only), else 1, 2 or 4. Part of the summation order:
+                                           frames only compare bit for bit at equal values                */
+  float local_radius;                   /* first radius (scene units) the local run table tries around a tile;
+                                           0 = from the scene's density                                   */
 } rdc_frame_params;
 
 void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t height, float rays_per_pixel);
+/* Grows the handle's scratch (partial sums of split work units, tile counters, the table of base directions, the
+ * frame buffers of rdc_render_frame_to_host when `host_frames` != 0) to what a frame of `params` needs. May allocate
+ * and synchronise the device. After it, rdc_render / rdc_render_to_frames / rdc_render_frame_to_host_async with
+ * parameters of at most this size and the same rays per pixel only enqueue; without it the first call at a new
+ * size does this work itself (and so synchronises once). */
+int rdc_scene_reserve(rdc_scene* scene, const rdc_frame_params* params, int host_frames, rdc_stream stream);
 /* image = float4[rows*W] (xyz written, w = 1), blur_map = float[rows*W]; both device pointers. */
 int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream);
 

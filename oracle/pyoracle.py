@@ -293,7 +293,7 @@ class SceneArrays(C.Structure):
 
 class AccelOptions(C.Structure):
     _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int),
-                ("run_length", C.c_int)]
+                ("run_length", C.c_int), ("shading_records", C.c_int)]
 
 
 class FrameParams(C.Structure):
@@ -304,6 +304,7 @@ class FrameParams(C.Structure):
         ("strip_stride", C.c_uint32), ("strip_offset", C.c_uint32),
         ("use_diffusion_curve_save", C.c_int), ("use_aa", C.c_int), ("max_trace_depth", C.c_int),
         ("traversal", C.c_int), ("hit_ids", C.c_void_p), ("max_sigma", C.c_void_p), ("stats", C.c_void_p),
+        ("route", C.c_int), ("units_per_tile", C.c_uint32), ("local_radius", C.c_float),
     ]
 
 
@@ -350,7 +351,7 @@ def make_params(width, height, rays_per_pixel, **kw) -> FrameParams:
 
 
 def make_accel(curve_width=1e-3, flatness_tolerance=0.05, max_chords_per_segment=1024) -> AccelOptions:
-    return AccelOptions(curve_width, flatness_tolerance, max_chords_per_segment, 0)
+    return AccelOptions(curve_width, flatness_tolerance, max_chords_per_segment, 0, 0)
 
 
 def build(verbose: bool = False) -> None:

@@ -50,7 +50,7 @@ class SceneArrays(C.Structure):
 
 class AccelOptions(C.Structure):
     _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int),
-                ("run_length", C.c_int)]
+                ("run_length", C.c_int), ("shading_records", C.c_int)]
 
 
 class SceneInfo(C.Structure):
@@ -69,11 +69,13 @@ class FrameParams(C.Structure):
         ("strip_stride", C.c_uint32), ("strip_offset", C.c_uint32),
         ("use_diffusion_curve_save", C.c_int), ("use_aa", C.c_int), ("max_trace_depth", C.c_int),
         ("traversal", C.c_int), ("hit_ids", C.c_void_p), ("max_sigma", C.c_void_p), ("stats", C.c_void_p),
+        ("route", C.c_int), ("units_per_tile", C.c_uint32), ("local_radius", C.c_float),
     ]
 
 
 TRAVERSAL_LBVH = 0
 TRAVERSAL_BRUTE_FORCE = 1
+ROUTE_AUTO, ROUTE_TREE, ROUTE_LOCAL_TABLE = 0, 1, 2
 
 # every symbol include/rdc_b200.h declares, with its prototype (tests check the library exports them all)
 PROTOTYPES = {
@@ -92,6 +94,7 @@ PROTOTYPES = {
     "rdc_scene_download_chords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rdc_scene_destroy": (None, [C.c_void_p]),
     "rdc_default_frame_params": (None, [C.POINTER(FrameParams), C.c_uint32, C.c_uint32, C.c_float]),
+    "rdc_scene_reserve": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_void_p]),
     "rdc_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "rdc_render_to_frames": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.c_void_p]),
@@ -320,6 +323,10 @@ class Scene:
         ids = np.empty((n, 3), np.uint32)
         _check(_lib.rdc_scene_download_chords(self._h, geom.ctypes.data, ids.ctypes.data), "rdc_scene_download_chords")
         return geom, ids
+
+    def reserve(self, params: FrameParams, host_frames: bool = False, stream: int = 0) -> None:
+        """rdc_scene_reserve: allocate the handle's scratch for frames like `params` ahead of the first render."""
+        _check(_lib.rdc_scene_reserve(self._h, C.byref(params), int(host_frames), C.c_void_p(stream)), "rdc_scene_reserve")
 
     def render(self, params: FrameParams, image_ptr: int, blur_map_ptr: int, stream: int = 0) -> None:
         """Enqueue one frame (rows [row_begin,row_end)) on `stream`. Pointers are device addresses."""

@@ -335,6 +335,7 @@ void destroy_scene(rdc_scene* s) {
       cudaEventDestroy(s->copied[k]);
     }
   }
+  if (s->launched) cudaEventDestroy(s->launched);
   cudaFree(s->frame_scratch);
   cudaFree(s->frame_sigma);
   cudaFree(s->part_rgbw);
@@ -368,11 +369,32 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
           set_error("accel: stop list %d of curve %u runs past its array", f, c);
           return RDC_E_INVALID;
         }
-    for (uint32_t c = 0; c < a.n_curves; ++c)
-      if (a.curve_connect[c] >= (int32_t)a.n_curves) {
+    // segments of a curve are consecutive: curve c owns [curve_map_inverse[c], next curve's first segment)
+    std::vector<uint32_t> seg_count(a.n_curves, 0u);
+    for (uint32_t sg = 0; sg < a.n_segments; ++sg) {
+      const uint32_t c = a.curve_map[sg];
+      if (c >= a.n_curves || a.curve_map_inverse[c] > sg || a.curve_index[sg] != sg - a.curve_map_inverse[c]) {
+        set_error("accel: segment %u does not sit at its ordinal inside its curve (curve_map / curve_index / curve_map_inverse disagree)", sg);
+        return RDC_E_INVALID;
+      }
+      seg_count[c]++;
+    }
+    for (uint32_t c = 0; c < a.n_curves; ++c) {
+      if (a.curve_map_inverse[c] >= a.n_segments) {
+        set_error("accel: curve %u starts past the last segment", c);
+        return RDC_E_INVALID;
+      }
+      const int32_t target = a.curve_connect[c];
+      if (target >= (int32_t)a.n_curves) {
         set_error("accel: curve %u connects to a missing curve", c);
         return RDC_E_INVALID;
       }
+      // a portal hit on ordinal k continues from ordinal k of the target curve (DeviceCode.cu:228)
+      if (target >= 0 && seg_count[target] < seg_count[c]) {
+        set_error("accel: curve %u connects to curve %d, which has fewer segments", c, target);
+        return RDC_E_INVALID;
+      }
+    }
   }
   rdc_scene* s = new rdc_scene();
   cudaGetDevice(&s->device);
@@ -493,7 +515,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
     std::vector<uint4> hints(2 * (size_t)n_chords);
 #ifdef RDC_SHADE_RECORDS
     // the table only pays while it stays in L2 next to everything else: 32 MB at most (250 k chords)
-    const bool with_records = (size_t)n_chords * 128 <= (32u << 20) && getenv("RDC_B200_NO_RECORDS") == nullptr;
+    const bool with_records = (size_t)n_chords * 128 <= (32u << 20) && o.shading_records >= 0;
     std::vector<float4> records(with_records ? 8 * (size_t)n_chords : 0);
     const float* scalar_v[3] = {a.blur, a.weight, a.weight_degree};
     const float* colour_v[2] = {a.color_left, a.color_right};

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -48,13 +49,27 @@ bool put_vec(std::FILE* f, const std::vector<T>& v) {
   const uint64_t n = v.size();
   return std::fwrite(&n, sizeof n, 1, f) == 1 && (n == 0 || std::fwrite(v.data(), sizeof(T), n, f) == n);
 }
+// bytes between the read position and the end of the file: no element count of an untrusted header may ask for more
+uint64_t bytes_left(std::FILE* f) {
+  const long here = std::ftell(f);
+  if (here < 0 || std::fseek(f, 0, SEEK_END) != 0) return 0;
+  const long end = std::ftell(f);
+  std::fseek(f, here, SEEK_SET);
+  return end > here ? (uint64_t)(end - here) : 0;
+}
 template <class T>
 bool get_vec(std::FILE* f, std::vector<T>& v) {
   uint64_t n = 0;
-  if (std::fread(&n, sizeof n, 1, f) != 1 || n > (1ull << 32)) return false;
+  if (std::fread(&n, sizeof n, 1, f) != 1 || n > bytes_left(f) / sizeof(T)) return false;
   v.resize(n);
   return n == 0 || std::fread(v.data(), sizeof(T), n, f) == n;
 }
+struct FileCloser {
+  std::FILE* f;
+  ~FileCloser() {
+    if (f) std::fclose(f);
+  }
+};
 template <class Op>
 bool stop_list_io(std::FILE* f, rdc_host_scene::StopList& l, Op&& io) {
   return io(f, l.index) && io(f, l.value) && io(f, l.u);
@@ -168,31 +183,34 @@ int rdc_host_scene_load(const char* path, rdc_host_scene** out) {
     rdc::set_error("scene load: cannot open %s", path);
     return RDC_E_IO;
   }
+  FileCloser closer{f};  // closed on every path, exceptions included
   return guarded(RDC_E_PARSE, [&]() {
-    auto* s = new rdc_host_scene();
+    std::unique_ptr<rdc_host_scene> s(new rdc_host_scene());
     char magic[8];
-    int32_t dims[2];
+    int32_t dims[2] = {0, 0};
     auto get = [](std::FILE* fp, auto& v) { return get_vec(fp, v); };
     bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, kCacheMagic, 8) == 0 && std::fread(dims, sizeof dims, 1, f) == 1 &&
               std::fread(s->n_true, sizeof s->n_true, 1, f) == 1 && get_vec(f, s->vertices) && get_vec(f, s->segment_indices) &&
               get_vec(f, s->curve_map) && get_vec(f, s->curve_index) && get_vec(f, s->curve_map_inverse) && get_vec(f, s->curve_connect);
     for (rdc_host_scene::StopList* l : {&s->color_left, &s->color_right, &s->blur, &s->weight, &s->weight_degree}) ok = ok && stop_list_io(f, *l, get);
-    std::fclose(f);
-    // structural checks: the arrays must describe a consistent scene
+    // structural checks: the arrays must describe a consistent scene (rdc_accel_build checks the cross references)
     const size_t nseg = s->segment_indices.size(), ncurves = s->curve_connect.size();
-    ok = ok && nseg > 0 && ncurves > 0 && s->vertices.size() % 3 == 0 && s->curve_map.size() == nseg && s->curve_index.size() == nseg &&
-         s->curve_map_inverse.size() == ncurves;
-    for (rdc_host_scene::StopList* l : {&s->color_left, &s->color_right, &s->blur, &s->weight, &s->weight_degree})
-      ok = ok && l->index.size() == 2 * ncurves && l->value.size() == l->u.size() * (size_t)l->stride && l->u.size() >= 2;
+    ok = ok && dims[0] > 0 && dims[1] > 0 && nseg > 0 && ncurves > 0 && s->vertices.size() % 3 == 0 && s->curve_map.size() == nseg &&
+         s->curve_index.size() == nseg && s->curve_map_inverse.size() == ncurves;
+    const rdc_host_scene::StopList* lists[5] = {&s->color_left, &s->color_right, &s->blur, &s->weight, &s->weight_degree};
+    for (int k = 0; ok && k < 5; ++k) {
+      const rdc_host_scene::StopList* l = lists[k];
+      ok = l->index.size() == 2 * ncurves && l->value.size() == l->u.size() * (size_t)l->stride && l->u.size() >= 2 &&
+           (size_t)s->n_true[k] + 2 <= l->u.size();
+    }
     if (!ok) {
-      delete s;
       rdc::set_error("scene load: %s is not a scene cache of this version", path);
       return RDC_E_PARSE;
     }
     s->image_width = dims[0];
     s->image_height = dims[1];
     s->sealed = true;
-    *out = s;
+    *out = s.release();
     return 0;
   });
 }
@@ -220,6 +238,7 @@ void rdc_default_accel_options(rdc_accel_options* o) {
   o->flatness_tolerance = 0.05f;
   o->max_chords_per_segment = 1024;
   o->run_length = 0;
+  o->shading_records = 0;
 }
 
 int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out) {
@@ -274,6 +293,9 @@ void rdc_default_frame_params(rdc_frame_params* p, uint32_t width, uint32_t heig
   p->hit_ids = nullptr;
   p->max_sigma = nullptr;
   p->stats = nullptr;
+  p->route = RDC_ROUTE_AUTO;
+  p->units_per_tile = 0;
+  p->local_radius = 0.0f;
 }
 
 int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, float* blur_map, rdc_stream stream) {
@@ -341,6 +363,49 @@ void setupCurand(void* states, int width, int height, rdc_stream stream) {
   if (width <= 0 || height <= 0) rdc::set_error("setupCurand: bad size");
 }
 
+namespace {
+// copy stream, events and the grow-only device frames of rdc_render_frame_to_host(_async)
+int ensure_frame_buffers(rdc_scene* scene, size_t n, cudaStream_t st) {
+  if (!scene->copy_stream) {
+    RDC_CUDA(cudaStreamCreateWithFlags(&scene->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      RDC_CUDA(cudaEventCreateWithFlags(&scene->rendered[k], cudaEventDisableTiming));
+      RDC_CUDA(cudaEventCreateWithFlags(&scene->copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (n > scene->frame_pixels) {
+    RDC_CUDA(cudaStreamSynchronize(st));
+    RDC_CUDA(cudaStreamSynchronize(scene->copy_stream));
+    cudaFree(scene->frame_image[0]);
+    cudaFree(scene->frame_image[1]);
+    cudaFree(scene->frame_scratch);
+    cudaFree(scene->frame_sigma);
+    scene->frame_image[0] = scene->frame_image[1] = scene->frame_scratch = nullptr;
+    scene->frame_sigma = nullptr;
+    scene->frame_pixels = 0;
+    RDC_CUDA(cudaMalloc((void**)&scene->frame_image[0], n * sizeof(float4)));
+    RDC_CUDA(cudaMalloc((void**)&scene->frame_image[1], n * sizeof(float4)));
+    RDC_CUDA(cudaMalloc((void**)&scene->frame_scratch, n * sizeof(float4)));
+    RDC_CUDA(cudaMalloc((void**)&scene->frame_sigma, (n + 1) * sizeof(float)));
+    scene->frame_pixels = n;
+  }
+  return 0;
+}
+}  // namespace
+
+int rdc_scene_reserve(rdc_scene* scene, const rdc_frame_params* params, int host_frames, rdc_stream stream) {
+  if (!scene || !params) {
+    rdc::set_error("reserve: null argument");
+    return RDC_E_INVALID;
+  }
+  return guarded(RDC_E_INVALID, [&]() {
+    int rc = rdc::reserve(scene, *params, (cudaStream_t)stream);
+    if (rc == 0 && host_frames)
+      rc = ensure_frame_buffers(scene, (size_t)(params->row_end - params->row_begin) * params->image_width, (cudaStream_t)stream);
+    return rc;
+  });
+}
+
 // Enqueue-only frame: render -> [blur] on `stream`, then the copy to host memory on the handle's own copy
 // stream, so that the copy of frame f overlaps the rendering of frame f+1 (two device images, used in turn).
 int rdc_render_frame_to_host_async(rdc_scene* scene, const rdc_frame_params* params, int use_blur, float* host_image,
@@ -357,29 +422,7 @@ int rdc_render_frame_to_host_async(rdc_scene* scene, const rdc_frame_params* par
     }
     const size_t rows = params->row_end - params->row_begin;
     const size_t n = rows * params->image_width;
-    if (!scene->copy_stream) {
-      RDC_CUDA(cudaStreamCreateWithFlags(&scene->copy_stream, cudaStreamNonBlocking));
-      for (int k = 0; k < 2; ++k) {
-        RDC_CUDA(cudaEventCreateWithFlags(&scene->rendered[k], cudaEventDisableTiming));
-        RDC_CUDA(cudaEventCreateWithFlags(&scene->copied[k], cudaEventDisableTiming));
-      }
-    }
-    if (n > scene->frame_pixels) {  // grow-only frame buffers owned by the handle
-      RDC_CUDA(cudaStreamSynchronize(st));
-      RDC_CUDA(cudaStreamSynchronize(scene->copy_stream));
-      cudaFree(scene->frame_image[0]);
-      cudaFree(scene->frame_image[1]);
-      cudaFree(scene->frame_scratch);
-      cudaFree(scene->frame_sigma);
-      scene->frame_image[0] = scene->frame_image[1] = scene->frame_scratch = nullptr;
-      scene->frame_sigma = nullptr;
-      scene->frame_pixels = 0;
-      RDC_CUDA(cudaMalloc((void**)&scene->frame_image[0], n * sizeof(float4)));
-      RDC_CUDA(cudaMalloc((void**)&scene->frame_image[1], n * sizeof(float4)));
-      RDC_CUDA(cudaMalloc((void**)&scene->frame_scratch, n * sizeof(float4)));
-      RDC_CUDA(cudaMalloc((void**)&scene->frame_sigma, (n + 1) * sizeof(float)));
-      scene->frame_pixels = n;
-    }
+    if (int rc = ensure_frame_buffers(scene, n, st)) return rc;  // grow-only; rdc_scene_reserve does it ahead of time
     const int slot = scene->frame_slot ^= 1;
     float4* image = scene->frame_image[slot];
     float* sigma = scene->frame_sigma;

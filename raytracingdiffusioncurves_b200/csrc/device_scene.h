@@ -92,6 +92,10 @@ struct rdc_scene {
   uint32_t base_dirs_capacity = 0;
   float* zero_sigma = nullptr;  // device float used when the caller passes no max_sigma
   unsigned int* work_counters = nullptr;  // k_render's tile counter pair (one render in flight per handle)
+  // the handle's launches are serialised: a launch on another stream waits for this event first
+  cudaEvent_t launched = nullptr;
+  cudaStream_t launched_on = nullptr;
+  bool launched_any = false;
   uint32_t grid_blocks[32] = {};  // SM-filling grid size per kernel variant
   float mean_run_w = 0.0f, mean_run_h = 0.0f;  // mean padded run box (local-table radius estimate)
   // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
@@ -119,6 +123,7 @@ int download_chords(const rdc_scene* s, float* geom, uint32_t* ids);
 // render.cu
 int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream, uint32_t n_targets = 0,
            float* const* target_images = nullptr, float* const* target_blur_maps = nullptr);
+int reserve(rdc_scene* s, const rdc_frame_params& p, cudaStream_t stream);
 // blur.cu
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
                   int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows = -1);

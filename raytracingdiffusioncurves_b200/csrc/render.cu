@@ -1083,6 +1083,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         a.part_blur[q * part_stride + local_pixel] = blur;
       }
       __threadfence();
+      __syncwarp();  // every lane's partial sums are out before lane 0 announces the unit
       unsigned int arrived = 0;
       if (lane == 0) arrived = atomicAdd(a.tile_arrivals + tile, 1u);
       arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
@@ -1166,23 +1167,18 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   }
 }
 
-}  // namespace
+// Everything about a launch that follows from the scene and the frame parameters alone.
+struct LaunchPlan {
+  int n_iter = 0;
+  bool smem = false, portals = false, table = false, local = false;
+  float local_r0 = 0.0f;
+  size_t dyn = 0;
+  int variant = 0;
+  uint32_t split = 1, strip_stride = 1, strip_offset = 0, local_rows = 0, row_skew = 0, local_tiles = 0;
+  size_t local_pixels = 0;
+};
 
-int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream, uint32_t n_targets,
-           float* const* target_images, float* const* target_blur_maps) {
-  if (!s || (n_targets == 0 && (!image || !blur_map))) {
-    set_error("render: null argument");
-    return RDC_E_INVALID;
-  }
-  if (n_targets > RDC_MAX_FRAME_TARGETS || (n_targets > 0 && (!target_images || !target_blur_maps))) {
-    set_error("render: at most %d target frames", RDC_MAX_FRAME_TARGETS);
-    return RDC_E_INVALID;
-  }
-  for (uint32_t t = 0; t < n_targets; ++t)
-    if (!target_images[t] || !target_blur_maps[t]) {
-      set_error("render: target frame %u is null", t);
-      return RDC_E_INVALID;
-    }
+int check_params(const rdc_frame_params& p) {
   if (p.image_width == 0 || p.image_height == 0 || p.row_begin >= p.row_end || p.row_end > p.image_height) {
     set_error("render: bad image size or row band [%u,%u) of %u", p.row_begin, p.row_end, p.image_height);
     return RDC_E_INVALID;
@@ -1203,16 +1199,147 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     set_error("render: more than 2^32 pixels");
     return RDC_E_LIMIT;
   }
-  const int n_iter = (int)ceilf(p.number_of_rays_per_pixel);
-  if (s->base_dirs_n != p.number_of_rays_per_pixel) {
-    if ((uint32_t)n_iter > s->base_dirs_capacity) {
-      float2* fresh = nullptr;
-      RDC_CUDA(cudaMalloc(&fresh, (size_t)n_iter * sizeof(float2)));
-      s->allocations.push_back(fresh);
-      s->base_dirs = fresh;
-      s->base_dirs_capacity = (uint32_t)n_iter;
+  if (p.route < RDC_ROUTE_AUTO || p.route > RDC_ROUTE_LOCAL_TABLE) {
+    set_error("render: unknown route %d", p.route);
+    return RDC_E_INVALID;
+  }
+  if (p.units_per_tile != 0 && p.units_per_tile != 1 && p.units_per_tile != 2 && p.units_per_tile != 4) {
+    set_error("render: units_per_tile must be 0 (automatic), 1, 2 or 4");
+    return RDC_E_INVALID;
+  }
+  if (!(p.local_radius >= 0.0f)) {
+    set_error("render: local_radius must be 0 (automatic) or positive");
+    return RDC_E_INVALID;
+  }
+  return 0;
+}
+
+LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
+  LaunchPlan L;
+  L.n_iter = (int)ceilf(p.number_of_rays_per_pixel);
+  L.strip_stride = p.strip_stride > 1 ? p.strip_stride : 1;
+  L.strip_offset = p.strip_stride > 1 ? p.strip_offset : 0;
+  const uint32_t rows = p.row_end - p.row_begin;
+  const uint32_t strips = (rows + kStripRows - 1) / kStripRows;  // of the band; this call renders those with t % stride == offset
+  const uint32_t my_strips = L.strip_offset < strips ? (strips - L.strip_offset + L.strip_stride - 1) / L.strip_stride : 0;
+  L.local_rows = L.strip_stride > 1 ? my_strips * kStripRows : rows;
+  L.row_skew = L.strip_stride > 1 ? 0u : p.row_begin % kWarpTileH;  // strips: give row_begin as a multiple of 4 for split-independent bits
+  const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
+  L.smem = scene_bytes <= kSmemSceneLimit;
+  L.portals = s->info.has_portals != 0;
+  const bool brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
+  // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
+  const bool masks_ok = (float)L.n_iter == p.number_of_rays_per_pixel && L.n_iter >= 8 && !brute && p.route != RDC_ROUTE_TREE;
+  //  * the whole scene in one table: at most 64 runs;
+  L.table = masks_ok && L.smem && s->dev.n_runs <= kTableRuns;
+  //  * a table per tile of the runs around it: larger scenes, unless the view is zoomed out so far that a tile's
+  //    own footprint already meets more runs than the table holds. First radius: the one at which a scene of
+  //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
+  //    mean run box w x h; the kernel adapts it per tile.
+  // measured on the bundled scenes: below 1024 runs the tree is as fast or faster (RDC_ROUTE_LOCAL_TABLE overrides)
+  const uint32_t local_min_runs = p.route == RDC_ROUTE_LOCAL_TABLE ? kTableRuns + 1 : 1024;
+  if (masks_ok && !L.table && s->dev.n_runs >= local_min_runs && s->dev.n_runs > kTableRuns) {
+    const float4 rb = s->dev.root_box;
+    const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
+    const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;
+    const double pa = (kWarpTileW - 1) * z + 2 * jit + s->mean_run_w, pb = (kWarpTileH - 1) * z + 2 * jit + s->mean_run_h;
+    const double per_run = area / s->dev.n_runs;  // scene area per run
+    if (area > 0.0 && pa * pb < 0.5 * kLocalSlots * per_run) {
+      const double disc = (pa + pb) * (pa + pb) - 4.0 * (pa * pb - 1.25 * kLocalSlots * per_run);
+      L.local_r0 = (float)((std::sqrt(disc) - (pa + pb)) * 0.25);
+      L.local = L.local_r0 > 0.0f && std::isfinite(L.local_r0);
     }
-    k_base_dirs<<<1, 32, 0, stream>>>(s->base_dirs, n_iter, 2 / p.number_of_rays_per_pixel);
+  }
+  if (L.local && p.local_radius > 0.0f) L.local_r0 = p.local_radius;
+  L.dyn = (L.smem ? scene_bytes + (L.table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
+          (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0);
+  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table
+  L.variant = (L.smem ? 1 : 0) | ((L.portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (L.table ? 8 : 0) | (L.local ? 16 : 0);
+  // Units per tile. It must not depend on how the frame is divided among GPUs (the summation order is part of
+  // the result), so it is a function of the full frame only: enough for about 200 k units in the frame (40 per
+  // warp of one GPU; every unit pays for its run table, and at 3840x2160 one unit per tile measured 8 % faster
+  // than four), at most kMaxSplit, while each unit keeps at least 16 rays and the partial sums fit 2 GiB.
+  const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
+  const uint64_t frame_tiles = (uint64_t)tiles_x * ((p.image_height + kWarpTileH - 1) / kWarpTileH);
+  uint32_t split = 1;
+  while (split < (uint32_t)kMaxSplit && frame_tiles * split < 200000ull) split <<= 1;
+  if (p.units_per_tile) split = p.units_per_tile;
+  // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
+  while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
+  L.split = split;
+  L.local_pixels = (size_t)L.local_rows * p.image_width;
+  L.local_tiles = tiles_x * ((L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH);
+  return L;
+}
+
+// Scratch a launch of this plan needs; grows only. Allocating means a device-wide synchronisation (cudaFree), which
+// is why rdc_scene_reserve exists.
+int ensure_capacity(rdc_scene* s, const LaunchPlan& L, cudaStream_t stream) {
+  if ((uint32_t)L.n_iter > s->base_dirs_capacity) {
+    float2* fresh = nullptr;
+    RDC_CUDA(cudaMalloc(&fresh, (size_t)L.n_iter * sizeof(float2)));
+    s->allocations.push_back(fresh);  // the old table may still be read by a launch in flight: freed with the handle
+    s->base_dirs = fresh;
+    s->base_dirs_capacity = (uint32_t)L.n_iter;
+    s->base_dirs_n = -1.0f;
+  }
+  if (L.split > 1 && (L.local_pixels * L.split > s->part_capacity || L.local_tiles > s->tile_capacity)) {
+    if (s->launched) RDC_CUDA(cudaEventSynchronize(s->launched));
+    cudaFree(s->part_rgbw);
+    cudaFree(s->part_blur);
+    cudaFree(s->tile_arrivals);
+    s->part_rgbw = nullptr; s->part_blur = nullptr; s->tile_arrivals = nullptr;
+    s->part_capacity = 0; s->tile_capacity = 0;
+    const size_t want = L.local_pixels * L.split;
+    RDC_CUDA(cudaMalloc((void**)&s->part_rgbw, want * sizeof(float4)));
+    RDC_CUDA(cudaMalloc((void**)&s->part_blur, want * sizeof(float)));
+    RDC_CUDA(cudaMalloc((void**)&s->tile_arrivals, L.local_tiles * sizeof(unsigned int)));
+    RDC_CUDA(cudaMemsetAsync(s->tile_arrivals, 0, L.local_tiles * sizeof(unsigned int), stream));
+    s->part_capacity = want;
+    s->tile_capacity = L.local_tiles;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int reserve(rdc_scene* s, const rdc_frame_params& p, cudaStream_t stream) {
+  if (!s) {
+    set_error("reserve: null argument");
+    return RDC_E_INVALID;
+  }
+  if (int rc = check_params(p)) return rc;
+  // the widest plan the parameters can lead to: the counting build and both routes share the same scratch sizes
+  const LaunchPlan L = plan_launch(s, p);
+  if (L.local_rows == 0) return 0;
+  return ensure_capacity(s, L, stream);
+}
+
+int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_map, cudaStream_t stream, uint32_t n_targets,
+           float* const* target_images, float* const* target_blur_maps) {
+  if (!s || (n_targets == 0 && (!image || !blur_map))) {
+    set_error("render: null argument");
+    return RDC_E_INVALID;
+  }
+  if (n_targets > RDC_MAX_FRAME_TARGETS || (n_targets > 0 && (!target_images || !target_blur_maps))) {
+    set_error("render: at most %d target frames", RDC_MAX_FRAME_TARGETS);
+    return RDC_E_INVALID;
+  }
+  for (uint32_t t = 0; t < n_targets; ++t)
+    if (!target_images[t] || !target_blur_maps[t]) {
+      set_error("render: target frame %u is null", t);
+      return RDC_E_INVALID;
+    }
+  if (int rc = check_params(p)) return rc;
+  const LaunchPlan L = plan_launch(s, p);
+  if (L.local_rows == 0) return 0;
+  if (int rc = ensure_capacity(s, L, stream)) return rc;
+  // One launch at a time per handle (shared work counters, partial sums, base directions): a launch on another
+  // stream waits — on the device — for the handle's previous one.
+  if (!s->launched) RDC_CUDA(cudaEventCreateWithFlags(&s->launched, cudaEventDisableTiming));
+  if (s->launched_any && s->launched_on != stream) RDC_CUDA(cudaStreamWaitEvent(stream, s->launched, 0));
+  if (s->base_dirs_n != p.number_of_rays_per_pixel) {
+    k_base_dirs<<<1, 32, 0, stream>>>(s->base_dirs, L.n_iter, 2 / p.number_of_rays_per_pixel);
     RDC_CUDA(cudaGetLastError());
     s->base_dirs_n = p.number_of_rays_per_pixel;
   }
@@ -1221,7 +1348,11 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.sc = s->dev;
   a.image = image;
   a.blur_map = blur_map;
-  a.discard_partials = getenv("RDC_B200_KEEP_PARTIALS") == nullptr;  // the variable only exists to measure the difference
+#ifdef RDC_KEEP_PARTIALS  // only exists to measure the difference (profiles/r01c_discard_partials.log)
+  a.discard_partials = 0;
+#else
+  a.discard_partials = 1;
+#endif
   a.n_targets = n_targets;
   for (uint32_t t = 0; t < n_targets; ++t) {
     a.target_image[t] = reinterpret_cast<float4*>(target_images[t]);
@@ -1235,9 +1366,9 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.height = p.image_height;
   a.row_begin = p.row_begin;
   a.row_end = p.row_end;
-  a.strip_stride = p.strip_stride > 1 ? p.strip_stride : 1;
-  a.strip_offset = p.strip_stride > 1 ? p.strip_offset : 0;
-  a.n_iter = n_iter;
+  a.strip_stride = L.strip_stride;
+  a.strip_offset = L.strip_offset;
+  a.n_iter = L.n_iter;
   a.n_rays = p.number_of_rays_per_pixel;
   a.two_over_n = 2 / p.number_of_rays_per_pixel;
   a.zoom = p.zoom_factor;
@@ -1250,50 +1381,12 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.max_depth = p.max_trace_depth;
   a.brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
   a.cull = p.traversal == RDC_TRAVERSAL_LBVH;  // the brute-force kernel really tests every ray against every chord
-
-  const uint32_t rows = p.row_end - p.row_begin;
-  const uint32_t strips = (rows + kStripRows - 1) / kStripRows;  // of the band; this call renders those with t % stride == offset
-  const uint32_t my_strips = a.strip_offset < strips ? (strips - a.strip_offset + a.strip_stride - 1) / a.strip_stride : 0;
-  if (my_strips == 0) return 0;
-  a.local_rows = a.strip_stride > 1 ? my_strips * kStripRows : rows;
-  a.row_skew = a.strip_stride > 1 ? 0u : p.row_begin % kWarpTileH;  // strips: give row_begin as a multiple of 4 for split-independent bits
+  a.local_rows = L.local_rows;
+  a.row_skew = L.row_skew;
+  a.local_r0 = L.local_r0;
   a.work = s->work_counters;
-  const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
-  size_t smem_limit = kSmemSceneLimit;
-  if (const char* env = getenv("RDC_B200_SMEM_LIMIT")) smem_limit = (size_t)atol(env);  // tuning experiments only
-  const bool smem = scene_bytes <= smem_limit;
-  const bool portals = s->info.has_portals != 0;
-  // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
-  const bool masks_ok = (float)n_iter == p.number_of_rays_per_pixel && n_iter >= 8 && !a.brute;
-  //  * the whole scene in one table: at most 64 runs;
-  const bool table = masks_ok && smem && s->dev.n_runs <= kTableRuns && getenv("RDC_B200_NO_TABLE") == nullptr;
-  //  * a table per tile of the runs around it: larger scenes, unless the view is zoomed out so far that a tile's
-  //    own footprint already meets more runs than the table holds. First radius: the one at which a scene of
-  //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
-  //    mean run box w x h; the kernel adapts it per tile.
-  bool local = false;
-  uint32_t local_min_runs = 1024;  // measured on the bundled scenes: below this the tree is as fast or faster
-  if (const char* env = getenv("RDC_B200_LOCAL_MIN_RUNS")) local_min_runs = (uint32_t)atoi(env);  // tuning experiments only
-  if (masks_ok && !table && s->dev.n_runs >= local_min_runs && s->dev.n_runs > kTableRuns && getenv("RDC_B200_NO_LOCAL") == nullptr) {
-    const float4 rb = s->dev.root_box;
-    const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
-    const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;
-    const double pa = (kWarpTileW - 1) * z + 2 * jit + s->mean_run_w, pb = (kWarpTileH - 1) * z + 2 * jit + s->mean_run_h;
-    const double per_run = area / s->dev.n_runs;  // scene area per run
-    if (area > 0.0 && pa * pb < 0.5 * kLocalSlots * per_run) {
-      const double disc = (pa + pb) * (pa + pb) - 4.0 * (pa * pb - 1.25 * kLocalSlots * per_run);
-      a.local_r0 = (float)((std::sqrt(disc) - (pa + pb)) * 0.25);
-      local = a.local_r0 > 0.0f && std::isfinite(a.local_r0);
-    }
-  }
-  if (const char* env = getenv("RDC_B200_LOCAL_R0")) {  // tuning experiments only
-    const float v = (float)atof(env);
-    if (local && v > 0.0f) a.local_r0 = v;
-  }
-  const size_t dyn = (smem ? scene_bytes + (table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
-                     (local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0);
-  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table
-  const int variant = (smem ? 1 : 0) | ((portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (table ? 8 : 0) | (local ? 16 : 0);
+  const int variant = L.variant;
+  const size_t dyn = L.dyn;
   void (*kernel)(RenderArgs) = nullptr;
   switch (variant) {
     case 0: kernel = k_render<false, false, false, kModeTree>; break;
@@ -1315,8 +1408,8 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
       set_error("render: no kernel variant %d", variant);
       return RDC_E_INVALID;
   }
-  if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
+    if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 0, sms = 0;
     RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
     RDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
@@ -1326,46 +1419,21 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
     }
     s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
   }
-  // Units per tile. It must not depend on how the frame is divided among GPUs (the summation order is part of
-  // the result), so it is a function of the full frame only: enough for about 200 k units in the frame (40 per
-  // warp of one GPU; every unit pays for its run table, and at 3840x2160 one unit per tile measured 8 % faster
-  // than four), at most kMaxSplit, while each unit keeps at least 16 rays and the partial sums fit 2 GiB.
-  const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
-  const uint64_t frame_tiles = (uint64_t)tiles_x * ((p.image_height + kWarpTileH - 1) / kWarpTileH);
-  uint32_t split = 1;
-  while (split < (uint32_t)kMaxSplit && frame_tiles * split < 200000ull) split <<= 1;
-  if (const char* env = getenv("RDC_B200_SPLIT")) {  // tuning experiments only
-    int v = atoi(env);
-    if (v == 1 || v == 2 || v == 4) split = (uint32_t)v;
-  }
-  // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
-  while (split > 1 && ((uint32_t)n_iter < (local ? 64u : 16u) * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
-  a.split = split;
-  const size_t local_pixels = (size_t)a.local_rows * p.image_width;
-  const uint32_t local_tiles = tiles_x * ((a.local_rows + a.row_skew + kWarpTileH - 1) / kWarpTileH);
-  if (split > 1 && (local_pixels * split > s->part_capacity || local_tiles > s->tile_capacity)) {
-    RDC_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(s->part_rgbw);
-    cudaFree(s->part_blur);
-    cudaFree(s->tile_arrivals);
-    s->part_rgbw = nullptr; s->part_blur = nullptr; s->tile_arrivals = nullptr;
-    s->part_capacity = 0; s->tile_capacity = 0;
-    RDC_CUDA(cudaMalloc((void**)&s->part_rgbw, local_pixels * split * sizeof(float4)));
-    RDC_CUDA(cudaMalloc((void**)&s->part_blur, local_pixels * split * sizeof(float)));
-    RDC_CUDA(cudaMalloc((void**)&s->tile_arrivals, local_tiles * sizeof(unsigned int)));
-    RDC_CUDA(cudaMemsetAsync(s->tile_arrivals, 0, local_tiles * sizeof(unsigned int), stream));
-    s->part_capacity = local_pixels * split;
-    s->tile_capacity = local_tiles;
-  }
+  a.split = L.split;
   a.part_rgbw = s->part_rgbw;
   a.part_blur = s->part_blur;
   a.tile_arrivals = s->tile_arrivals;
-  const uint32_t warp_tiles = local_tiles * split;
+  const uint32_t warp_tiles = L.local_tiles * L.split;
   uint32_t grid = s->grid_blocks[variant];
   const uint32_t needed = (warp_tiles + kBlock / 32 - 1) / (kBlock / 32);
   if (grid > needed) grid = needed;
+  // the work counters rewind themselves when a launch ends; a launch that was cut short must not poison the next
+  RDC_CUDA(cudaMemsetAsync(s->work_counters, 0, 2 * sizeof(unsigned int), stream));
   kernel<<<grid, kBlock, dyn, stream>>>(a);
   RDC_CUDA(cudaGetLastError());
+  RDC_CUDA(cudaEventRecord(s->launched, stream));
+  s->launched_on = stream;
+  s->launched_any = true;
   return 0;
 }
 

@@ -57,6 +57,21 @@ def test_product_does_not_reference_the_oracle():
                                      text, flags=re.M), f"{f} reaches into oracle/"
 
 
+def test_library_reads_no_environment_variables():
+    """SURVEY.md 8(b) "no global mutable state": every switch is a struct field, nothing is read from the environment."""
+    pkg = os.path.join(ROOT, "raytracingdiffusioncurves_b200", "csrc")
+    for f in os.listdir(pkg):
+        if f.endswith((".h", ".cpp", ".cu")) and f != "optixhello_main.cpp":
+            assert "getenv" not in open(os.path.join(pkg, f), errors="replace").read(), f"{f} reads the environment"
+
+
+def test_route_and_unit_fields_are_validated():
+    p = api.default_frame_params(64, 64, 16)
+    assert (p.route, p.units_per_tile, p.local_radius) == (api.ROUTE_AUTO, 0, 0.0)
+    a = api.default_accel_options()
+    assert a.shading_records == 0
+
+
 def test_view_helpers_follow_the_glfw_callbacks():
     p = api.default_frame_params(64, 64, 8)
     api.lib.rdc_view_scroll(ctypes.byref(p), 1.0)          # glfw_events.cpp:110: zoom *= 1.5^-yoffset

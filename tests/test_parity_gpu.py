@@ -335,14 +335,14 @@ LOCAL_VIEWS = [("DiffusionCurvePack/dolphin.xml", 0.25, 0.0, 0.0, 16), ("Diffusi
 
 
 @pytest.mark.parametrize("name,zoom,off_x,off_y,n", LOCAL_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[1]}" for v in LOCAL_VIEWS])
-def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle, monkeypatch):
+def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle):
     """Close-up views of the larger scenes: primary rays settled by the per-tile table of nearby runs, the rest
     deferred to the tree — every first hit still the oracle's brute-force closest chord."""
-    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")  # the library keeps scenes this small on the tree (it is faster there)
     path = os.path.join(xml_dir, name)
     scene = po.ingest_xml(path, True)
     w, h = 72, 52  # not a multiple of the 8x4 tile
-    p = po.make_params(w, h, n, zoom_factor=zoom, offset_x=off_x, offset_y=off_y)
+    # route: left to itself the library keeps scenes this small on the tree (it is faster there)
+    p = po.make_params(w, h, n, zoom_factor=zoom, offset_x=off_x, offset_y=off_y, route=api.ROUTE_LOCAL_TABLE)
     oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
     r = GpuRenderer(path)
     out = r.render(product_params(api, p), want_hits=True)
@@ -360,16 +360,15 @@ def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_o
         assert deferred < traced
 
 
-def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path, monkeypatch):
+def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path):
     """Config 5 in miniature at its own scale (one pixel = one scene unit): the local-table path on a dense scene."""
-    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")
     xml = api.synth_xml(3000, 1024, 1024)
     f = tmp_path / "synth.xml"
     f.write_bytes(xml)
     scene = po.ingest_xml(str(f), True)
     r = GpuRenderer(str(f))
     for off_x, off_y, n in ((0.0, 0.0, 16), (300.0, -250.0, 32), (-480.0, 470.0, 8)):
-        p = po.make_params(64, 48, n, zoom_factor=1.0, offset_x=off_x, offset_y=off_y)
+        p = po.make_params(64, 48, n, zoom_factor=1.0, offset_x=off_x, offset_y=off_y, route=api.ROUTE_LOCAL_TABLE)
         oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
         out = r.render(product_params(api, p), want_hits=True, want_stats=True)
         assert np.array_equal(out["hits"], ohits)
@@ -380,16 +379,16 @@ def test_local_run_table_synthetic_close_up(api, port_oracle, tmp_path, monkeypa
         assert np.array_equal(plain["hits"], ohits)
         # the same frame in two bands: bit-identical pixels (the table depends on the tile only)
         parts = [r.render(product_params(api, po.make_params(64, 48, n, zoom_factor=1.0, offset_x=off_x, offset_y=off_y,
-                                                               row_begin=b, row_end=e))) for b, e in ((0, 16), (16, 48))]
+                                                               route=api.ROUTE_LOCAL_TABLE, row_begin=b, row_end=e)))
+                 for b, e in ((0, 16), (16, 48))]
         assert np.array_equal(bits(np.concatenate([q["image"] for q in parts])), bits(plain["image"]))
 
 
-def test_local_run_table_with_portals(api, port_oracle, tmp_path, monkeypatch):
+def test_local_run_table_with_portals(api, port_oracle, tmp_path):
     """The local-table kernel on a scene that has `connects` curves: primary hits settled by the table continue
     through portals on the tree; deferred rays do the same."""
     import re
 
-    monkeypatch.setenv("RDC_B200_LOCAL_MIN_RUNS", "65")
     xml = api.synth_xml(1500, 512, 512).decode()
     count = [0]
 
@@ -409,7 +408,8 @@ def test_local_run_table_with_portals(api, port_oracle, tmp_path, monkeypatch):
     assert (scene["curve_connect"] >= 0).sum() == 300
     r = GpuRenderer(str(f))
     for depth in (0, 2, 31):
-        p = po.make_params(64, 48, 16, zoom_factor=1.0, offset_x=20.0, offset_y=-30.0, max_trace_depth=depth)
+        p = po.make_params(64, 48, 16, zoom_factor=1.0, offset_x=20.0, offset_y=-30.0, max_trace_depth=depth,
+                           route=api.ROUTE_LOCAL_TABLE)
         oimg, oblur, ohits = port_oracle.render(scene, p, want_hits=True)
         out = r.render(product_params(api, p), want_hits=True, want_stats=True)
         assert np.array_equal(out["hits"], ohits)

@@ -15,7 +15,7 @@ from helpers import all_scene_files, XML_DIR  # noqa: E402
 from raytracingdiffusioncurves_b200 import api  # noqa: E402
 
 
-def time_frames(scene, width, height, rpp, zoom, frames=3):
+def time_frames(scene, width, height, rpp, zoom, frames=3, route=0):
     stream = torch.cuda.current_stream().cuda_stream
     image = torch.empty((height, width, 4), dtype=torch.float32, device="cuda")
     sigma = torch.empty((height, width), dtype=torch.float32, device="cuda")
@@ -25,7 +25,7 @@ def time_frames(scene, width, height, rpp, zoom, frames=3):
     best = None
     for f in range(frames):
         flag.zero_()
-        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, frame=f)
+        p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, frame=f, route=route)
         p.max_sigma = flag.data_ptr()
         t0.record()
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
@@ -56,10 +56,8 @@ def main():
                "blur_ms": round(blur_ms, 3), "max_sigma": round(smax, 2),
                "grays_per_s": round(width * height * rpp / (render_ms + blur_ms) / 1e6, 2)}
         if modes:
-            os.environ["RDC_B200_NO_LOCAL"] = "1"
-            os.environ["RDC_B200_NO_TABLE"] = "1"
-            row["tree_render_ms"] = round(time_frames(scene, width, height, rpp, zoom)[0], 3)
-            del os.environ["RDC_B200_NO_LOCAL"], os.environ["RDC_B200_NO_TABLE"]
+            row["tree_render_ms"] = round(time_frames(scene, width, height, rpp, zoom, route=api.ROUTE_TREE)[0], 3)
+            row["local_render_ms"] = round(time_frames(scene, width, height, rpp, zoom, route=api.ROUTE_LOCAL_TABLE)[0], 3)
         total += render_ms + blur_ms
         rows.append(row)
         print(json.dumps(row), flush=True)
