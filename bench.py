@@ -137,8 +137,29 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_oracle_run(kind_pref, scene_spec, width, height, rpp, depth, zoom, target_seconds):
-    """Times the CPU implementation on a bounded band of the workload. Returns the cpu_baseline dict."""
+def workload_config(name, n_gpus):
+    """What both arms print under "config": the workload, nothing that varies from run to run."""
+    spec, width, height, rpp, depth = WORKLOADS[name]
+    return {"workload": name, "scene": spec, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
+            "orzan": True, "max_trace_depth": depth, "zoom": workload_zoom(spec, height),
+            "parallelism": "single GPU" if n_gpus == 1 else f"{RDC_STRIP_ROWS}-row strips dealt round-robin over {n_gpus} GPUs, frame on rank 0",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+RDC_STRIP_ROWS = 8  # include/rdc_b200.h
+
+
+def host_threads():
+    """Host threads the CPU arm may use: the process's affinity mask, NOT OMP_NUM_THREADS (torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would put the CPU arm on one core and inflate every N > 1 ratio)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_oracle_run(kind_pref, scene_spec, width, height, rpp, depth, zoom, target_seconds, whole_frame=False):
+    """Times the CPU implementation on a bounded band of the workload (or the whole frame). Returns the cpu_baseline dict."""
     from oracle import pyoracle as po
 
     kind = kind_pref if (kind_pref == "port" or po.Oracle.reference_available()) else "port"
@@ -159,15 +180,19 @@ def cpu_oracle_run(kind_pref, scene_spec, width, height, rpp, depth, zoom, targe
         b = max(0, mid - rows // 2)
         p = po.make_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, row_begin=b, row_end=min(height, b + rows))
         t0 = time.perf_counter()
-        oracle.render(scene, p)
+        oracle.render(scene, p, threads=threads)
         return time.perf_counter() - t0, (p.row_end - p.row_begin)
 
-    t_probe, rows_probe = run(max(oracle.threads(), 8))
-    rows = int(max(rows_probe, min(height, rows_probe * target_seconds / max(t_probe, 1e-6))))
-    t, rows = run(rows)
+    threads = host_threads()
+    if whole_frame:
+        t, rows = run(height)
+    else:
+        t_probe, rows_probe = run(max(threads, 8))
+        rows = int(max(rows_probe, min(height, rows_probe * target_seconds / max(t_probe, 1e-6))))
+        t, rows = run(rows)
     rays = float(rows) * width * rpp
     return {
-        "value": rays / t / 1e9, "unit": "Grays/s", "cores": oracle.threads(),
+        "value": rays / t / 1e9, "unit": "Grays/s", "cores": threads,
         "kind": "reference" if kind == "reference" else "port",
         "sample": f"{rows} centre rows of the {width}x{height}@{rpp} frame ({rays / 1e6:.1f} M rays, {t:.1f} s), render only, "
                   + ("reference DeviceCode.cu compiled for the host (oracle/_ref)" if kind == "reference"
@@ -183,10 +208,14 @@ def run_reference(args):
         return
     spec, width, height, rpp, depth = WORKLOADS[args.workload]
     zoom = workload_zoom(spec, height)
-    per_step_seconds = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    # a step is one whole frame while that keeps the run within a few minutes (the headline frame takes ~4 s on 16 threads);
+    # for the heavier workloads each step is a band of the frame sized from a probe
+    per_step_seconds = max(1.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    probe = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, 1.0)
+    whole = probe["ms_per_frame_extrapolated"] * 1e-3 * (args.steps + args.warmup) <= 240.0
     results = []
     for i in range(args.warmup + args.steps):
-        r = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, per_step_seconds)
+        r = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, per_step_seconds, whole_frame=whole)
         if i >= args.warmup:
             results.append(r)
     value = sum(r["value"] for r in results) / len(results)
@@ -196,8 +225,10 @@ def run_reference(args):
         "impl": "reference", "metric": "Grays/s", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(width) * height * rpp / (value * 1e9) * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "bundled scene file" if spec.startswith("xml:") else "synthetic",
-        "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp,
-                   "note": "each step times a bounded band of the frame on the host cores; ms_per_step is the extrapolated full frame"},
+        "config": workload_config(args.workload, args.gpus),
+        "details": {"step": "one whole frame on the host cores" if whole else
+                    "a bounded band of the frame on the host cores; ms_per_step is the extrapolated full frame",
+                    "threads_from": "os.sched_getaffinity (OMP_NUM_THREADS is ignored: torchrun sets it to 1)"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -222,10 +253,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
-    if "RDC_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["RDC_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout; keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG"):
+        # NCCL logs to stdout unless told otherwise; stdout carries the one JSON line, so its log (rank counts included) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -490,11 +520,10 @@ def main():
             "metric": "Grays/s", "value": value, "unit": "Grays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
-            "config": {"workload": args.workload, "width": width, "height": height, "rays_per_pixel": rpp, "blur": True, "aa": True,
-                       "orzan": True, "max_trace_depth": depth, "zoom": zoom, "curves": st.n_curves, "segments": st.n_segments,
-                       "chords": st.n_chords, "bvh_depth": st.bvh_depth, "parallelism": f"8-row strips dealt round-robin over {world} GPUs, to rank 0 through {exchange}" if world > 1 else "single GPU",
-                       "runs": st.n_runs, "l2": "flushed between timed steps (256 MiB write)", "setup_ms": setup_ms,
-                       "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+            "config": workload_config(args.workload, world),
+            "details": {"curves": st.n_curves, "segments": st.n_segments, "chords": st.n_chords, "runs": st.n_runs, "bvh_depth": st.bvh_depth,
+                        "exchange": exchange if world > 1 else None, "setup_ms": setup_ms,
+                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
             "clocks": sampler.result(),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps * world,

@@ -166,9 +166,14 @@ void render_pixel(const Ctx& c, uint32_t ix, uint32_t iy, uint32_t local_row, fl
 
 }  // namespace
 
+namespace {
+int g_search = 0;  // 0: every chord per ray; 1: through the uniform grid of oracle_common.h (same answer, checked in tests/)
+}
+
 extern "C" {
 
 int oracle_threads(void) { return omp_get_max_threads(); }
+void oracle_set_search(int mode) { g_search = mode; }
 
 // chord list in original order; geom = 4 floats, ids = 3 uint32 (segment, k, K) per chord.
 // Call with geom == NULL to get the count.
@@ -188,6 +193,7 @@ int oracle_chords(const rdc_scene_arrays* a, const rdc_accel_options* o, float* 
 int oracle_render(const rdc_scene_arrays* a, const rdc_accel_options* o, const rdc_frame_params* p, float* image,
                   float* blur_map, uint32_t* hit_ids, int threads) {
   ChordSet cs = oracle::build_chords(*a, *o);
+  if (g_search == 1) oracle::build_grid(cs);
   Ctx c{*a, *p, cs};
   if (threads <= 0) threads = omp_get_max_threads();
   // rows of the band, or (strip_stride > 1) the strips t % stride == offset of it, packed (rdc_b200.h)
@@ -201,6 +207,23 @@ int oracle_render(const rdc_scene_arrays* a, const rdc_accel_options* o, const r
     const uint32_t rel = iy - p->row_begin;
     const uint32_t local_row = (rel / RDC_STRIP_ROWS / stride) * RDC_STRIP_ROWS + rel % RDC_STRIP_ROWS;
     for (uint32_t ix = 0; ix < p->image_width; ++ix) render_pixel(c, ix, iy, local_row, image, blur_map, hit_ids);
+  }
+  return 0;
+}
+
+// Closest hit of arbitrary primary rays (rays = n x {ox, oy, dx, dy}); id = chord id or 0xFFFFFFFF, t = ray
+// parameter, u = segment parameter of the hit ((k + s) / K). Feeds the geometry check of the chord intersector
+// against a double-precision ray/B-spline root (tests/test_intersector_geometry_cpu.py).
+int oracle_trace_rays(const rdc_scene_arrays* a, const rdc_accel_options* o, const float* rays, uint32_t n, uint32_t* id,
+                      float* t, float* u) {
+  ChordSet cs = oracle::build_chords(*a, *o);
+  if (g_search == 1) oracle::build_grid(cs);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (uint32_t i = 0; i < n; ++i) {
+    const Hit h = oracle::closest_hit(cs, rays[4 * i], rays[4 * i + 1], rays[4 * i + 2], rays[4 * i + 3], true, 1u, 0u);
+    id[i] = h.id;
+    t[i] = h.t;
+    u[i] = h.valid() ? rdc_hit_u(cs.chords[h.id].k, cs.chords[h.id].K, h.s) : 0.0f;
   }
   return 0;
 }

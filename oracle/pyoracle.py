@@ -381,6 +381,8 @@ class Oracle:
         self._render.restype = C.c_int
         self._threads = self.lib.oracle_threads if kind == "port" else self.lib.ref_threads
         self._threads.restype = C.c_int
+        self._set_search = self.lib.oracle_set_search if kind == "port" else self.lib.ref_set_search
+        self._set_search.argtypes = [C.c_int]
         if kind == "port":
             self.lib.oracle_chords.argtypes = [C.POINTER(SceneArrays), C.POINTER(AccelOptions), C.c_void_p, C.c_void_p, u32p]
             self.lib.oracle_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -393,7 +395,10 @@ class Oracle:
         return int(self._threads())
 
     def render(self, scene: dict, params: FrameParams, accel: AccelOptions | None = None, want_hits: bool = False,
-               threads: int = 0):
+               threads: int = 0, search: str = "brute"):
+        """search: 'brute' tests every chord per ray; 'grid' narrows the candidates with a uniform grid first (same
+        closest hit, bit for bit — tests/test_oracle_cpu.py — and the only way through scenes of a million chords)."""
+        self._set_search({"brute": 0, "grid": 1}[search])
         accel = accel or make_accel()
         a, keep = arrays_from_dict(scene)
         rows = params.row_end - params.row_begin
@@ -408,6 +413,21 @@ class Oracle:
             raise RuntimeError(f"{self.kind} oracle render returned {rc}")
         del keep
         return image, blur_map, hits
+
+    def trace_rays(self, scene: dict, rays: np.ndarray, accel: AccelOptions | None = None, search: str = "brute"):
+        """Closest hit of n primary rays (rays[n,4] = ox, oy, dx, dy): (chord id, t, segment parameter u)."""
+        assert self.kind == "port"
+        self._set_search({"brute": 0, "grid": 1}[search])
+        accel = accel or make_accel()
+        a, keep = arrays_from_dict(scene)
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = len(rays)
+        ids, t, u = np.empty(n, np.uint32), np.empty(n, np.float32), np.empty(n, np.float32)
+        self.lib.oracle_trace_rays.argtypes = [C.POINTER(SceneArrays), C.POINTER(AccelOptions), C.c_void_p, C.c_uint32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+        self.lib.oracle_trace_rays(C.byref(a), C.byref(accel), rays.ctypes.data, n, ids.ctypes.data, t.ctypes.data, u.ctypes.data)
+        del keep
+        return ids, t, u
 
     def chords(self, scene: dict, accel: AccelOptions | None = None):
         assert self.kind == "port"

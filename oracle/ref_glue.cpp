@@ -122,6 +122,8 @@ void optixTrace(OptixTraversableHandle, float3 o, float3 d, float, float, float,
 extern "C" {
 
 int ref_threads(void) { return omp_get_max_threads(); }
+static int g_search = 0;  // 0: every chord per ray; 1: through the uniform grid of oracle_common.h
+void ref_set_search(int mode) { g_search = mode; }
 
 // the switches the reference was compiled with
 void ref_switches(int* use_diffusion_curve_save, int* use_aa, int* max_trace_depth) {
@@ -138,6 +140,7 @@ int ref_render(const rdc_scene_arrays* a, const rdc_accel_options* o, const rdc_
       p->max_trace_depth != MAX_TRACE_DEPTH || p->strip_stride > 1)
     return -1;
   oracle::ChordSet cs = oracle::build_chords(*a, *o);
+  if (g_search == 1) oracle::build_grid(cs);
   const size_t n_vertices = a->n_vertices;
   std::vector<float3> vertices(n_vertices);
   for (size_t i = 0; i < n_vertices; ++i) vertices[i] = float3{a->vertices[3 * i], a->vertices[3 * i + 1], a->vertices[3 * i + 2]};

@@ -118,3 +118,31 @@ def test_blur_restatement_properties(port_oracle):
     expect[10:21] = wts / wts.sum()
     np.testing.assert_allclose(out, expect, atol=1e-6)
     assert out[9] == 0 and out[21] == 0
+
+
+GRID_VIEWS = [("arch.xml", 64, 48, 32, 512 / 48, 0.0, 0.0, 2), ("PortalDemo.xml", 64, 48, 24, 512 / 48, 0.0, 0.0, 31),
+              ("DiffusionCurvePack/dolphin.xml", 48, 36, 16, 0.5, 60.0, -40.0, 2),
+              ("DiffusionCurvePack/dolphin.xml", 40, 30, 8, 633 / 30, 0.0, 0.0, 2),
+              ("DiffusionCurvePack/roses_spirales.xml", 40, 30, 16, 0.75, 0.0, 0.0, 2),
+              ("DiffusionCurvePack/lady_bug.xml", 40, 30, 16, 4.0, -30.0, 20.0, 2)]
+
+
+@pytest.mark.parametrize("name,w,h,n,zoom,off_x,off_y,depth", GRID_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[4]:.2f}" for v in GRID_VIEWS])
+def test_grid_search_equals_brute_force(name, w, h, n, zoom, off_x, off_y, depth, xml_dir, port_oracle):
+    """The uniform grid (oracle_common.h) only narrows which chords a ray is tested against: same closest hit,
+    same image, bit for bit, as testing every chord — which is what lets the full-size parity tests use it."""
+    scene = po.ingest_xml(os.path.join(xml_dir, name), True)
+    p = po.make_params(w, h, n, zoom_factor=zoom, offset_x=off_x, offset_y=off_y, max_trace_depth=depth)
+    a = port_oracle.render(scene, p, want_hits=True, search="brute")
+    b = port_oracle.render(scene, p, want_hits=True, search="grid")
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(bits(a[0]), bits(b[0])) and np.array_equal(bits(a[1]), bits(b[1]))
+    assert (a[2] != 0xFFFFFFFF).any()
+
+
+def test_grid_search_equals_brute_force_reference_build(xml_dir, ref_oracle):
+    scene = po.ingest_xml(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"), True)
+    p = po.make_params(40, 30, 16, zoom_factor=2.0, offset_x=10.0, offset_y=5.0)
+    a = ref_oracle.render(scene, p, want_hits=True, search="brute")
+    b = ref_oracle.render(scene, p, want_hits=True, search="grid")
+    assert np.array_equal(a[2], b[2]) and np.array_equal(bits(a[0]), bits(b[0]))
