@@ -14,7 +14,6 @@ python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo 
 prof() {  # name, env assignments..., then "--", then the command
   local name=$1; shift
   env "$@" > $OUT/plain_$name.log 2>&1 &&
-  env "$@" > /dev/null 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render --launch-skip 1 -c 1 -f -o $OUT/prof_$name \
     env "$@" > $OUT/ncu_$name.log 2>&1
   echo "$name: ncu exit $?" >> $OUT/ncu_status.log
