@@ -15,7 +15,7 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Iinclude
 
 LIB       := $(PKG)/librdc_b200.so
 CLI       := $(PKG)/OptixHello
-CU_SRCS   := $(CSRC)/accel.cu $(CSRC)/render.cu $(CSRC)/blur.cu $(CSRC)/capi.cu $(CSRC)/microbench.cu $(CSRC)/extras.cu
+CU_SRCS   := $(CSRC)/accel.cu $(CSRC)/render.cu $(CSRC)/blur.cu $(CSRC)/capi.cu $(CSRC)/microbench.cu $(CSRC)/extras.cu $(CSRC)/peer.cu
 CPP_SRCS  := $(CSRC)/xml_dom.cpp $(CSRC)/ingest.cpp $(CSRC)/synth.cpp $(CSRC)/jpeg.cpp
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.cpp.o,$(CPP_SRCS))
@@ -32,7 +32,7 @@ $(BUILD)/%.cpp.o: $(CSRC)/%.cpp $(HEADERS)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lrt
 
 $(CLI): $(CSRC)/optixhello_main.cpp $(LIB) $(HEADERS)
 	$(CXX) $(CXXFLAGS) -o $@ $< -L$(PKG) -lrdc_b200 -Wl,-rpath,'$$ORIGIN' -I/usr/local/cuda/include -L/usr/local/cuda/lib64 -lcudart

@@ -174,6 +174,49 @@ int rdc_render(rdc_scene* scene, const rdc_frame_params* params, float* image, f
 int rdc_render_to_frames(rdc_scene* scene, const rdc_frame_params* params, uint32_t n_targets, float* const* images,
                          float* const* blur_maps, rdc_stream stream);
 
+/* ---- one frame over the GPUs of a box, all in C: frames the ranks share, a barrier in peer memory,
+ *      and the per-frame drivers. A "rank" is one GPU with its own rdc_scene (scene and tree are replicated); ranks may
+ *      live in one process (one host thread enqueueing on every device: rdc_peer_frames_connect_local) or in one process
+ *      each (rdc_peer_frames_export / _connect_ipc: CUDA IPC handles, carried by whatever the launcher offers). The
+ *      frame loop these replace is optixHello.cpp:1163-1259. world <= RDC_MAX_FRAME_TARGETS. ---- */
+typedef struct rdc_peer_frames rdc_peer_frames;
+#define RDC_PEER_HANDLE_BYTES 320 /* five 64-byte cudaIpcMemHandle_t per rank */
+/* allocates this rank's buffers on the current device (rendered frame + sigma, two finished frames, flags) */
+int rdc_peer_frames_create(uint32_t width, uint32_t height, int rank, int world, rdc_peer_frames** out);
+int rdc_peer_frames_export(const rdc_peer_frames* frames, void* handle_bytes /* RDC_PEER_HANDLE_BYTES */);
+/* all_handles: world * RDC_PEER_HANDLE_BYTES, rank-major (the rank's own entry is ignored) */
+int rdc_peer_frames_connect_ipc(rdc_peer_frames* frames, const void* all_handles);
+/* same process: all[r] was created as rank r on its own device; enables peer access both ways */
+int rdc_peer_frames_connect_local(rdc_peer_frames* const* all, int world);
+void rdc_peer_frames_destroy(rdc_peer_frames* frames);
+/* All ranks' streams meet: work enqueued before it on any rank is complete and visible to every rank's work after it.
+ * Enqueue-only (one tiny kernel: flags in peer memory, release/acquire at system scope); every rank must call it the
+ * same number of times. A rank that never arrives raises an error flag after ~4 s instead of wedging the GPU
+ * (rdc_peer_status, synchronous, reports it). */
+int rdc_peer_barrier(rdc_peer_frames* frames, rdc_stream stream);
+int rdc_peer_status(rdc_peer_frames* frames);
+/* Device consumer: every rank renders its strips and stores them straight into the consumers' frames over NVLink; the
+ * finished frame (blurred when use_blur and halo_rows > 0; halo_rows >= ceil(3 * largest sigma)) ends in one of rank 0's
+ * two frame buffers, used in turn: *frame_out (rank 0; NULL elsewhere). `wait_event` (cudaEvent_t or NULL) is waited for
+ * on `stream` right before the frame's first barrier: rank 0 passes "the consumer of the frame returned two calls ago is
+ * done", because the peers start writing that buffer after this barrier. Enqueue-only. */
+int rdc_peer_render_frame(rdc_scene* scene, rdc_peer_frames* frames, const rdc_frame_params* params, int use_blur,
+                          int halo_rows, void* wait_event, rdc_stream stream, float** frame_out);
+/* Host consumer: nothing is gathered on a GPU — every rank copies its own rows of the finished frame over its own PCIe
+ * link into `host_frame`, ONE full frame float4[H*W] in pinned host memory that every rank addresses (rdc_host_frame_open
+ * when the ranks are processes). Enqueue-only; the copy runs on the handle's copy stream and overlaps the next frame's
+ * rendering. rdc_peer_frames_wait blocks until this rank's copies have landed. Use two host frames in turn. */
+int rdc_peer_frame_to_host(rdc_scene* scene, rdc_peer_frames* frames, const rdc_frame_params* params, int use_blur,
+                           int halo_rows, float* host_frame, rdc_stream stream);
+int rdc_peer_frames_wait(rdc_peer_frames* frames);
+/* A host frame all ranks can address: POSIX shared memory `name` (create != 0 on one rank, then 0 on the others),
+ * mapped and registered with CUDA as pinned memory. */
+int rdc_host_frame_open(const char* name, size_t bytes, int create, float** out);
+int rdc_host_frame_close(const char* name, float* frame, size_t bytes, int unlink_it);
+/* ceil(3 * largest blur value a frame of this scene can hold) — the blur's reach in rows (helperKernels.cu:65,74);
+ * each portal passed multiplies sigma by another stop (DeviceCode.cu:311). 0: the scene has no blur. */
+int rdc_host_scene_halo_rows(const rdc_host_scene* scene, int max_trace_depth, int* halo_rows);
+
 /* ---- helper kernels: same names and signatures as helperKernels.cu's extern "C" launchers
  *      (declared at optixHello.cpp:51-54) ---- */
 #ifndef RDC_NO_REFERENCE_HELPER_NAMES

@@ -98,6 +98,20 @@ PROTOTYPES = {
     "rdc_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "rdc_render_to_frames": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.c_void_p]),
+    "rdc_peer_frames_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "rdc_peer_frames_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rdc_peer_frames_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rdc_peer_frames_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "rdc_peer_frames_destroy": (None, [C.c_void_p]),
+    "rdc_peer_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rdc_peer_status": (C.c_int, [C.c_void_p]),
+    "rdc_peer_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_void_p)]),
+    "rdc_peer_frame_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(FrameParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rdc_peer_frames_wait": (C.c_int, [C.c_void_p]),
+    "rdc_host_frame_open": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "rdc_host_frame_close": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "rdc_host_scene_halo_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "gaussianBlur": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "setFloatDevice": (None, [C.c_void_p, C.c_uint, C.c_float, C.c_void_p]),
     "setupCurand": (None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -212,6 +226,12 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+    def halo_rows(self, max_trace_depth: int = 0) -> int:
+        """rdc_host_scene_halo_rows: the blur's reach in rows for any frame of this scene (0: no blur)."""
+        out = C.c_int()
+        _check(_lib.rdc_host_scene_halo_rows(self._h, max_trace_depth, C.byref(out)), "rdc_host_scene_halo_rows")
+        return out.value
 
     def max_blur(self, max_trace_depth: int = 0) -> float:
         """Upper bound of any blur_map value: sigma is a weighted mean of blur stops; each portal passed
@@ -357,6 +377,88 @@ def _scene_wait(self):
 
 Scene.render_frame_to_host_async = _scene_async
 Scene.frame_wait = _scene_wait
+
+
+PEER_HANDLE_BYTES = 320  # RDC_PEER_HANDLE_BYTES
+
+
+class PeerFrames:
+    """One rank's view of the frames the GPUs of a box share (rdc_peer_frames_*). Pointer marshalling only."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int):
+        h = C.c_void_p()
+        _check(_lib.rdc_peer_frames_create(width, height, rank, world, C.byref(h)), "rdc_peer_frames_create")
+        self._h, self.rank, self.world, self.width, self.height = h, rank, world, width, height
+
+    def export_handles(self) -> bytes:
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _check(_lib.rdc_peer_frames_export(self._h, buf), "rdc_peer_frames_export")
+        return buf.raw
+
+    def connect_ipc(self, all_handles: bytes) -> None:
+        assert len(all_handles) == PEER_HANDLE_BYTES * self.world
+        _check(_lib.rdc_peer_frames_connect_ipc(self._h, all_handles), "rdc_peer_frames_connect_ipc")
+
+    @staticmethod
+    def connect_local(frames) -> None:
+        arr = (C.c_void_p * len(frames))(*[f._h for f in frames])
+        _check(_lib.rdc_peer_frames_connect_local(arr, len(frames)), "rdc_peer_frames_connect_local")
+
+    def barrier(self, stream: int = 0) -> None:
+        _check(_lib.rdc_peer_barrier(self._h, C.c_void_p(stream)), "rdc_peer_barrier")
+
+    def status(self) -> None:
+        _check(_lib.rdc_peer_status(self._h), "rdc_peer_status")
+
+    def render_frame(self, scene: "Scene", params: FrameParams, use_blur: bool, halo_rows: int, stream: int = 0,
+                     wait_event: int = 0) -> int:
+        """Device consumer: returns the device address of the finished frame on rank 0, 0 elsewhere."""
+        out = C.c_void_p()
+        _check(_lib.rdc_peer_render_frame(scene.handle, self._h, C.byref(params), int(use_blur), halo_rows, C.c_void_p(wait_event),
+                                          C.c_void_p(stream), C.byref(out)), "rdc_peer_render_frame")
+        return out.value or 0
+
+    def frame_to_host(self, scene: "Scene", params: FrameParams, use_blur: bool, halo_rows: int, host_frame_ptr: int,
+                      stream: int = 0) -> None:
+        _check(_lib.rdc_peer_frame_to_host(scene.handle, self._h, C.byref(params), int(use_blur), halo_rows,
+                                           C.c_void_p(host_frame_ptr), C.c_void_p(stream)), "rdc_peer_frame_to_host")
+
+    def wait(self) -> None:
+        _check(_lib.rdc_peer_frames_wait(self._h), "rdc_peer_frames_wait")
+
+    def close(self) -> None:
+        if self._h:
+            _lib.rdc_peer_frames_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostFrame:
+    """A host frame every rank of a box can address: POSIX shared memory, pinned (rdc_host_frame_open)."""
+
+    def __init__(self, name: str, nbytes: int, create: bool):
+        p = C.c_void_p()
+        _check(_lib.rdc_host_frame_open(name.encode(), nbytes, int(create), C.byref(p)), "rdc_host_frame_open")
+        self.name, self.nbytes, self.ptr, self.owner = name, nbytes, p.value, create
+
+    def numpy(self, shape):
+        return np.ctypeslib.as_array(C.cast(self.ptr, f32p), shape=(self.nbytes // 4,)).reshape(shape)
+
+    def close(self) -> None:
+        if self.ptr:
+            _lib.rdc_host_frame_close(self.name.encode(), C.c_void_p(self.ptr), self.nbytes, int(self.owner))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def gaussian_blur(dest_ptr: int, src_ptr: int, sigma_ptr: int, scratch_ptr: int, width: int, height: int,

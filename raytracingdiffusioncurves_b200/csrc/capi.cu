@@ -148,6 +148,22 @@ int rdc_host_scene_arrays(const rdc_host_scene* scene, rdc_scene_arrays* out) {
 
 void rdc_host_scene_destroy(rdc_host_scene* scene) { delete scene; }
 
+int rdc_host_scene_halo_rows(const rdc_host_scene* scene, int max_trace_depth, int* halo_rows) {
+  if (!scene || !halo_rows || max_trace_depth < 0) {
+    rdc::set_error("halo rows: bad argument");
+    return RDC_E_INVALID;
+  }
+  float m = 0.0f;
+  for (uint32_t i = 0; i < scene->n_true[2]; ++i) m = std::fmax(m, scene->blur.value[i]);
+  bool portals = false;
+  for (int32_t c : scene->curve_connect) portals |= c >= 0;
+  double reach = m;
+  if (portals && m > 1.0f) reach = std::pow((double)m, max_trace_depth + 1);
+  const double rows = std::ceil(3.0 * reach);
+  *halo_rows = rows > 1e6 ? 1000000 : (int)rows;
+  return 0;
+}
+
 int rdc_host_scene_save(const rdc_host_scene* scene, const char* path) {
   if (!scene || !path) {
     rdc::set_error("scene save: null argument");
