@@ -9,13 +9,15 @@ A "step" is one frame of the hot path: ray generation + closest-hit traversal + 
 xmls/arch.xml at 1920x1080, 128 rays per pixel, Orzan flag / blur / per-ray jitter as shipped, denoiser
 off. The metric is Grays/s = primary rays per second (W*H*rpp / t_frame / 1e9), whole job.
 
-N > 1: the image is dealt out in 8-row strips, round-robin over the ranks (scene + tree replicated). The
-frame reaches rank 0 through peer memory: the render kernel of every rank stores its finished pixels straight
-into rank 0's frame over NVLink (rdc_render_to_frames on symmetric memory), then one barrier; scenes with blur
-store the rendered frame into every rank's buffer, every rank blurs one contiguous band and the blur stores it
-into rank 0's frame (raytracingdiffusioncurves_b200/distributed.py: render_frame_peer). Where symmetric memory
-cannot be set up, or with RDC_BENCH_NCCL=1, the same split runs on NCCL gather / all-gather (render_frame).
-Total work is fixed as N grows ("strong" scaling); every exchange is inside the timed region.
+N > 1: the image is dealt out in 8-row strips, round-robin over the ranks (scene + tree replicated). All of it runs
+through the C ABI (csrc/peer.cu; torch.distributed only carries the CUDA IPC handles at set-up, the timing reductions and
+host barriers). `value`: the frame reaches rank 0's device through peer memory — the render kernel of every rank stores
+its finished pixels straight into rank 0's frame over NVLink, then one barrier kernel; scenes with blur store the rendered
+frame into every rank's buffer, every rank blurs one contiguous band and the blur stores it into rank 0's frame
+(rdc_peer_render_frame). `e2e`: host consumer — every rank copies its own rows of the finished frame over its own PCIe link
+into one pinned host frame shared by all ranks (rdc_peer_frame_to_host). Total work is fixed as N grows ("strong" scaling);
+every exchange is inside the timed region. After the headline measurement the same run renders a few frames of
+BASELINE.json configs[4] (8192x8192 @512, 100 k synthetic curves) at the same N and reports them under "secondary".
 
 Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
 """
@@ -65,6 +67,9 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the config-5 block (8192x8192 @512 synthetic scene) that follows the headline measurement")
+    ap.add_argument("--secondary-steps", type=int, default=2)
     return ap.parse_args()
 
 
@@ -236,13 +241,282 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def source_sha16():
+    """Hash of the sources the shipped library is built from; profiles/*_ncu.json records the one it was captured with."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "raytracingdiffusioncurves_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + ["../../include/rdc_b200.h", "../../Makefile"]:
+        path = os.path.join(csrc, f)
+        if os.path.isfile(path) and f.endswith((".cu", ".cpp", ".h", "Makefile")):
+            h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(workload):
+    """Per-launch DRAM bytes and issue-slot utilisation of k_render from the committed ncu capture of the SHIPPED build
+    (profiles/r02_ncu_k_render.json, written by tools/ncu_to_json.py from an .ncu-rep; never a constant in this file)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_k_render.json")) as fh:
+            doc = json.load(fh)
+    except Exception:
+        return None
+    rec = doc.get("captures", {}).get(workload)
+    if not rec:
+        return None
+    rec = dict(rec)
+    rec["source"] = "profiles/r02_ncu_k_render.json"
+    rec["captured_with_source_sha16"] = doc.get("source_sha16")
+    rec["same_sources_as_this_build"] = doc.get("source_sha16") == source_sha16()
+    return rec
+
+
+class Workload:
+    """One bench workload on this rank: scene + tree on the device, frame buffers, and the two per-frame calls
+    (device consumer for `value`, host consumer for `e2e`). N > 1 goes through the C ABI's peer frames (csrc/peer.cu)."""
+
+    def __init__(self, name, api, torch, dist, dev, rank, world):
+        self.name, self.api, self.torch, self.dist, self.dev, self.rank, self.world = name, api, torch, dist, dev, rank, world
+        self.spec, self.width, self.height, self.rpp, self.depth = WORKLOADS[name]
+        self.stream = torch.cuda.current_stream().cuda_stream
+        kind, payload = scene_source(self.spec)
+        self.kind = kind
+        t0 = time.perf_counter()
+        self.host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
+        self.ingest_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        self.scene = api.Scene(self.host.arrays, None, self.stream)
+        torch.cuda.synchronize()
+        self.build_ms = (time.perf_counter() - t0) * 1e3
+        self.zoom = float(self.host.arrays.image_height) / self.height  # SURVEY.md Appendix E
+        self.halo = self.host.halo_rows(self.depth)
+        self.flag = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.scene.reserve(self.params(0), world == 1, self.stream)
+        w, h = self.width, self.height
+        if world == 1:
+            self.band = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
+            self.sigma = torch.empty((h, w), dtype=torch.float32, device=dev)
+            self.scratch = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
+            self.out = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
+            self.exchange = None
+            self.launches_per_step = 3
+        else:
+            # frames shared by the ranks: allocated by the library, IPC handles exchanged over torch.distributed (plumbing)
+            self.peers = api.PeerFrames(w, h, rank, world)
+            mine = torch.frombuffer(bytearray(self.peers.export_handles()), dtype=torch.uint8).to(dev)
+            every = torch.empty((world * api.PEER_HANDLE_BYTES,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every, mine)
+            self.peers.connect_ipc(bytes(every.cpu().numpy().tobytes()))
+            dist.barrier()
+            my_strips = len(range(rank, (h + RDC_STRIP_ROWS - 1) // RDC_STRIP_ROWS, world))
+            self.band = torch.empty((max(1, my_strips) * RDC_STRIP_ROWS, w, 4), dtype=torch.float32, device=dev)  # roofline launches
+            self.sigma = torch.empty((max(1, my_strips) * RDC_STRIP_ROWS, w), dtype=torch.float32, device=dev)
+            self.exchange = ("C ABI peer frames (rdc_peer_render_frame): render kernel stores into the consumers' frames over NVLink, "
+                             "barrier kernel on flags in peer memory; CUDA IPC handles exchanged once at set-up")
+            self.launches_per_step = 2 + (3 if self.halo > 0 else 0)  # render + barrier [+ 2 blur kernels + barrier]
+
+    def params(self, step, **kw):
+        return self.api.default_frame_params(self.width, self.height, self.rpp, zoom_factor=self.zoom, max_trace_depth=self.depth,
+                                             frame=step, **kw)
+
+    def frame_step(self, step, wait_event=0):
+        """One frame, inputs resident, finished frame on (rank 0's) device."""
+        api = self.api
+        if self.world == 1:
+            self.flag.zero_()
+            p = self.params(step)
+            p.max_sigma = self.flag.data_ptr()
+            self.scene.render(p, self.band.data_ptr(), self.sigma.data_ptr(), self.stream)
+            api.gaussian_blur(self.out.data_ptr(), self.band.data_ptr(), self.sigma.data_ptr(), self.scratch.data_ptr(), self.width,
+                              self.height, 0, self.height, self.flag.data_ptr(), self.stream)
+            return self.out.data_ptr()
+        return self.peers.render_frame(self.scene, self.params(step), True, self.halo, self.stream, wait_event)
+
+    def my_share(self, step):
+        q = self.params(step)
+        if self.world > 1:
+            q.strip_stride, q.strip_offset = self.world, self.rank
+        return q
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def time_value(self, steps, warmup, flush, sampler=None):
+        """Device-timed frames, L2 flushed between them, max over ranks. Returns (ms per step, wall seconds)."""
+        torch = self.torch
+        for s in range(warmup):
+            self.frame_step(s)
+        if sampler:
+            sampler.start()  # (NVML start-up takes milliseconds and differs from rank to rank: keep it in front of the barrier)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()  # all ranks enter the timed region together: a rank that came early would count its wait for the others
+        wall0 = time.perf_counter()
+        for s in range(steps):
+            flush.zero_()  # evict L2 between timed iterations (untimed)
+            starts[s].record()
+            self.frame_step(warmup + s)
+            ends[s].record()
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join()
+        total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, ends))], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(total_ms, op=self.dist.ReduceOp.MAX)
+            self.peers.status()
+        return float(total_ms.item()) / steps, wall
+
+    def time_e2e(self, n):
+        """The same frames through host buffers: parameters in, finished frame in pinned host memory, every step; the copy of
+        one frame overlaps the rendering of the next (two host frames in turn). Returns (seconds per step, description)."""
+        torch, api = self.torch, self.api
+        w, h = self.width, self.height
+        if self.world == 1:
+            hosts = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+            for s in range(2):
+                self.scene.render_frame_to_host(self.params(s), True, hosts[0].data_ptr(), self.stream)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for s in range(n):
+                self.scene.render_frame_to_host_async(self.params(1000 + s), True, hosts[s % 2].data_ptr(), self.stream)
+            self.scene.frame_wait()
+            t = (time.perf_counter() - t0) / n
+            t0 = time.perf_counter()
+            for s in range(n):
+                self.scene.render_frame_to_host(self.params(2000 + s), True, hosts[0].data_ptr(), self.stream)
+            t_sync = (time.perf_counter() - t0) / n
+            return t, ("rdc_render_frame_to_host_async + rdc_frame_wait (render + blur + copy to pinned host memory, the copy of one "
+                       f"frame overlapping the next frame's rendering); frame-by-frame rdc_render_frame_to_host: {t_sync * 1e3:.3f} ms")
+        # one host frame all ranks address: POSIX shared memory created by rank 0, pinned in every process
+        names = [f"/rdc_bench_{os.getpid()}_{k}" for k in range(2)] if self.rank == 0 else [None, None]
+        self.dist.broadcast_object_list(names, src=0)
+        nbytes = h * w * 16
+        hosts = []
+        if self.rank == 0:
+            hosts = [api.HostFrame(nm, nbytes, True) for nm in names]
+        self.dist.barrier()
+        if self.rank != 0:
+            hosts = [api.HostFrame(nm, nbytes, False) for nm in names]
+        for s in range(2):
+            self.peers.frame_to_host(self.scene, self.params(s), True, self.halo, hosts[s % 2].ptr, self.stream)
+        self.peers.wait()
+        self.barrier()
+        t0 = time.perf_counter()
+        for s in range(n):
+            self.peers.frame_to_host(self.scene, self.params(1000 + s), True, self.halo, hosts[s % 2].ptr, self.stream)
+        self.peers.wait()  # this rank's rows of every frame are in host memory
+        self.barrier()     # ... and so are everybody else's
+        t_local = torch.tensor([(time.perf_counter() - t0) / n], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t_local, op=self.dist.ReduceOp.MAX)
+        self.e2e_check = None
+        if self.rank == 0:  # the assembled host frame is a finished frame: no row was left untouched
+            self.e2e_check = bool(np_isfinite_or_nan_rows(hosts[(n - 1) % 2].numpy((h, w, 4))))
+        self.dist.barrier()
+        for hf in hosts:
+            hf.close()
+        return float(t_local.item()), ("rdc_peer_frame_to_host + rdc_peer_frames_wait: every rank renders its strips and copies its own rows "
+                                       "of the finished frame over its own PCIe link into one pinned host frame shared by all ranks "
+                                       "(POSIX shared memory), the copies of one frame overlapping the next frame's rendering")
+
+    def kernel_roofline(self, reps):
+        """k_render alone on this rank's share: work per ray from the counting build, time from CUDA events on its stream."""
+        torch = self.torch
+        stats = torch.zeros((6,), dtype=torch.int64, device=self.dev)
+        my_rows = sum(min(RDC_STRIP_ROWS, self.height - t * RDC_STRIP_ROWS)
+                      for t in range(self.rank, (self.height + RDC_STRIP_ROWS - 1) // RDC_STRIP_ROWS, self.world)) if self.world > 1 else self.height
+        p = self.my_share(0)
+        p.stats = stats.data_ptr()
+        self.scene.render(p, self.band.data_ptr(), self.sigma.data_ptr(), self.stream)
+        torch.cuda.synchronize()
+        traced, nodes, chords, shaded, deferred, gathered = [float(x) for x in stats.cpu().tolist()]
+        nodes += gathered
+        rays = float(my_rows) * self.width * self.rpp
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pk = self.my_share(1)
+        pk.max_sigma = self.flag.data_ptr()
+        k0.record()
+        for _ in range(reps):
+            self.scene.render(pk, self.band.data_ptr(), self.sigma.data_ptr(), self.stream)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / reps
+        per = {"nodes": nodes / rays, "chords": chords / rays, "hits_shaded": shaded / rays, "rays_traced": traced / rays,
+               "deferred_to_tree": deferred / rays, "table_query_nodes": gathered / rays}
+        f_ray = F_GEN + per["nodes"] * F_NODE + per["chords"] * F_SEG + per["hits_shaded"] * F_SHADE + F_ACC
+        b_ray = per["nodes"] * 32.0 + per["chords"] * 32.0  # SURVEY.md 8d: L2-side bytes per ray
+        return {"rays": rays, "rows": my_rows, "kernel_ms": kernel_ms, "per_ray": per, "flops_per_ray": f_ray, "l2_bytes_per_ray": b_ray}
+
+    def close(self):
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            self.peers.close()
+
+
+def np_isfinite_or_nan_rows(frame):
+    """Every row of an assembled host frame was written: alpha is 1 everywhere (rdc_render writes w = 1; the blur keeps it)."""
+    import numpy as np
+
+    a = frame[..., 3]
+    return np.all(np.abs(a - 1.0) < 1e-3)
+
+
+def measure_peaks(api, torch, stream, dev):
+    """FP32 (dependent FFMA) and L2-read microbenchmarks on this GPU, now."""
+    sink = torch.zeros((4,), dtype=torch.float32, device=dev)
+    flops = ctypes.c_double()
+    api.lib.rdc_microbench_fp32(2048, 2, sink.data_ptr(), ctypes.byref(flops), stream)
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    api.lib.rdc_microbench_fp32(2048, 10, sink.data_ptr(), ctypes.byref(flops), stream)
+    m1.record()
+    torch.cuda.synchronize()
+    fp32 = flops.value * 10 / (m0.elapsed_time(m1) * 1e-3) / 1e12
+    buf = torch.zeros((32 << 20,), dtype=torch.uint8, device=dev)  # 32 MB: stays in L2
+    nbytes = ctypes.c_double()
+    api.lib.rdc_microbench_l2(buf.data_ptr(), buf.numel(), 4, 1, sink.data_ptr(), ctypes.byref(nbytes), stream)  # warm
+    torch.cuda.synchronize()
+    m0.record()
+    api.lib.rdc_microbench_l2(buf.data_ptr(), buf.numel(), 16, 4, sink.data_ptr(), ctypes.byref(nbytes), stream)
+    m1.record()
+    torch.cuda.synchronize()
+    l2 = nbytes.value * 4 / (m0.elapsed_time(m1) * 1e-3) / 1e9
+    return fp32, l2
+
+
+def roofline_block(work, k, fp32_peak, l2_peak, hbm_peak, single_gpu):
+    achieved = k["rays"] * k["flops_per_ray"] / (k["kernel_ms"] * 1e-3) / 1e12
+    l2_achieved = k["rays"] * k["l2_bytes_per_ray"] / (k["kernel_ms"] * 1e-3) / 1e9
+    alg_bytes = float(k["rows"]) * work.width * 20.0
+    cap = ncu_capture(work.name) if single_gpu else None
+    return {
+        "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+        "traffic": cap.get("dram_bytes") if cap else None,
+        "issue_slots": cap,
+        "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
+        "kernel_ms": k["kernel_ms"], "flops_per_ray": k["flops_per_ray"], "per_ray": k["per_ray"],
+        "l2": {"bytes_per_ray": k["l2_bytes_per_ray"], "achieved_gbs": l2_achieved, "peak_gbs": l2_peak, "frac": l2_achieved / l2_peak,
+               "peak_source": "L2-read microbenchmark (rdc_microbench_l2: 32 MB buffer, ld.global.cg, 128-bit loads) run in this process",
+               "note": "SURVEY.md 8d: rays * (boxes + chords) * 32 B / t / L2 peak; the larger of the fp32 and l2 fractions is the binding one"},
+        "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k["kernel_ms"] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": (alg_bytes / (k["kernel_ms"] * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; the partial sums of split work "
+                        "units stay in L2 (their lines are discarded once added up, see DESIGN.md 3.1)"},
+    }
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -259,276 +533,76 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # plumbing only: handle exchange, timing reductions, host barriers
     stream = torch.cuda.current_stream().cuda_stream
-
-    spec, width, height, rpp, depth = WORKLOADS[args.workload]
-    kind, payload = scene_source(spec)
-    t_setup = time.perf_counter()
-    host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
-    scene = api.Scene(host.arrays, None, stream)
-    torch.cuda.synchronize()
-    setup_ms = (time.perf_counter() - t_setup) * 1e3
-    zoom = float(host.arrays.image_height) / height  # the XML frame stays visible vertically
-
-    row_begin, row_end = api.row_band(height, rank, world)
-    rows = row_end - row_begin
-    flag = torch.zeros((1,), dtype=torch.float32, device=dev)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step_box = [0]
 
-    def params_for(step, b=row_begin, e=row_end, **kw):
-        return api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=step,
-                                        row_begin=b, row_end=e, **kw)
-
-    if world == 1:
-        band = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
-        sigma_band = torch.empty((height, width), dtype=torch.float32, device=dev)
-        scratch = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
-        out_frame = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
-
-        def frame_step(step):
-            """One frame, inputs resident: render -> blur."""
-            flag.zero_()
-            p = params_for(step)
-            p.max_sigma = flag.data_ptr()
-            scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
-            api.gaussian_blur(out_frame.data_ptr(), band.data_ptr(), sigma_band.data_ptr(), scratch.data_ptr(), width, height, 0,
-                              height, flag.data_ptr(), stream)
-            return out_frame
-        launches_per_step = 3
-    else:
-        from raytracingdiffusioncurves_b200 import distributed as rd
-
-        halo = rd.halo_rows(host.max_blur(depth))
-        plan = rd.StripPlan(height, width, world, rank, halo)
-        bands = rd.FrameBuffers(plan, dev)
-        render_strips, blur_rows = api.cuda_callbacks(scene, lambda: params_for(step_box[0], 0, height), stream)
-        band, sigma_band = bands.local_image, bands.local_sigma
-        # Peer-memory form (render kernel stores into the consumers' frames over NVLink, no NCCL on the data path) unless
-        # symmetric memory is unavailable on this box or RDC_BENCH_NCCL=1 asks for the NCCL gather.
-        peers, peer_error = None, None
-        if os.environ.get("RDC_BENCH_NCCL") != "1":
-            try:
-                peers = rd.PeerFrameBuffers(plan, dev)
-                render_to, blur_rows_peer = api.cuda_peer_callbacks(scene, lambda: params_for(step_box[0], 0, height), stream)
-            except Exception as exc:  # noqa: BLE001
-                peers, peer_error = None, f"{type(exc).__name__}: {exc}"
-        ok = torch.tensor([1 if peers is not None else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
-        if int(ok.item()) == 0:
-            peers = None
-        exchange = "peer memory (symmetric memory, stores from the render/blur kernels)" if peers is not None else \
-            "NCCL gather / all-gather" + (f" (peer path unavailable: {peer_error})" if peer_error else "")
-
-        hook_box = [None]  # e2e: rank 0's "the copy-out of the frame before last is done" wait (see render_frame_peer)
-
-        def frame_step(step):
-            """One frame over all ranks: render my strips -> (all-gather, local band blur) -> gather to rank 0."""
-            step_box[0] = step
-            if peers is not None:
-                return rd.render_frame_peer(peers, render_to, blur_rows_peer, use_blur=True, before_barrier=hook_box[0])
-            return rd.render_frame(bands, render_strips, blur_rows, use_blur=True)
-        launches_per_step = 1 + (2 if halo > 0 else 0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: device-timed, inputs resident, L2 flushed between steps ----------------------------
-    for s in range(args.warmup):
-        frame_step(s)
+    work = Workload(args.workload, api, torch, dist, dev, rank, world)
     sampler = ClockSampler(local_rank)
-    sampler.start()  # (NVML start-up takes milliseconds and differs from rank to rank: keep it in front of the barrier)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()  # all ranks enter the timed region together: a rank that came early would count its wait for the others
-    wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.zero_()  # evict L2 between timed iterations (untimed)
-        starts[s].record()
-        frame_step(args.warmup + s)
-        ends[s].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    sampler.stop_flag = True
-    sampler.join()
-    step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    rays_per_frame = float(width) * height * rpp
+    ms_per_step, wall = work.time_value(args.steps, args.warmup, flush, sampler)
+    rays_per_frame = float(work.width) * work.height * work.rpp
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host buffers in and out, every step ---------------------------------------------------
     n_e2e = max(3, min(args.steps, 50))
-    host_img = torch.empty((height, width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
-    if world == 1:
-        # the public host-buffer call: frame parameters in, pinned image out, every step. The pipelined form
-        # enqueues the copy of frame f on the handle's copy stream while frame f+1 renders; two pinned buffers
-        # are filled in turn, the clock stops when the last frame is in host memory.
-        host_imgs = [host_img, torch.empty((height, width, 4), dtype=torch.float32).pin_memory()]
-        for s in range(2):
-            scene.render_frame_to_host(params_for(s), True, host_img.data_ptr(), stream)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for s in range(n_e2e):
-            scene.render_frame_to_host_async(params_for(1000 + s), True, host_imgs[s % 2].data_ptr(), stream)
-        scene.frame_wait()
-        t_e2e = (time.perf_counter() - t0) / n_e2e
-        t0 = time.perf_counter()
-        for s in range(n_e2e):
-            scene.render_frame_to_host(params_for(2000 + s), True, host_img.data_ptr(), stream)
-        t_sync = (time.perf_counter() - t0) / n_e2e
-        e2e_api = ("rdc_render_frame_to_host_async + rdc_frame_wait (render + blur + copy to pinned host memory, the copy of one "
-                   f"frame overlapping the next frame's rendering); frame-by-frame rdc_render_frame_to_host: {t_sync * 1e3:.3f} ms")
-    else:
-        if peers is not None:
-            # pipelined like the single-GPU call: rank 0 copies frame f to pinned host memory on its own stream while
-            # frame f+1 is rendered into the other frame buffer; two pinned buffers in turn; the clock stops when the
-            # last frame is in host memory.
-            main, copy_stream = torch.cuda.current_stream(), torch.cuda.Stream()
-            host_imgs = [host_img, torch.empty((height, width, 4), dtype=torch.float32).pin_memory()] if rank == 0 else None
-            rendered = [torch.cuda.Event() for _ in range(2)]
-            copied = [torch.cuda.Event() for _ in range(2)]
-            count = [0]
-
-            def wait_for_copy_before_last():
-                c = count[0]
-                if rank == 0 and c >= 1:
-                    main.wait_event(copied[(c - 1) % 2])  # frame c-1's copy-out: its buffer is the next frame's target
-            hook_box[0] = wait_for_copy_before_last
-
-            def e2e_step(step):
-                frame = frame_step(step)
-                c = count[0]
-                if rank == 0:
-                    rendered[c % 2].record(main)
-                    copy_stream.wait_event(rendered[c % 2])
-                    with torch.cuda.stream(copy_stream):
-                        host_imgs[c % 2].copy_(frame, non_blocking=True)
-                        copied[c % 2].record(copy_stream)
-                count[0] = c + 1
-
-            def e2e_finish():
-                torch.cuda.synchronize()
-        else:
-            def e2e_step(step):
-                frame = frame_step(step)
-                if rank == 0:
-                    host_img.copy_(frame[:height], non_blocking=True)
-                torch.cuda.synchronize()
-
-            def e2e_finish():
-                pass
-        for s in range(2):
-            e2e_step(s)
-        e2e_finish()
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(n_e2e):
-            e2e_step(1000 + s)
-        e2e_finish()
-        barrier()
-        t_local = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-        t_e2e = float(t_local.item())
-        e2e_api = ("distributed.render_frame_peer" if peers is not None else "distributed.render_frame") + \
-            " (strip render, exchange, band blur, frame on rank 0) + copy of the frame to pinned host memory on rank 0" + \
-            (", the copy of one frame overlapping the next frame's rendering" if peers is not None else "")
+    t_e2e, e2e_api = work.time_e2e(n_e2e)
     e2e = {"value": rays_per_frame / t_e2e / 1e9, "unit": "Grays/s", "ms_per_step": t_e2e * 1e3,
-           "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams) * world, "d2h_bytes_per_step": height * width * 16, "steps": n_e2e,
-           "api": e2e_api}
+           "h2d_bytes_per_step": ctypes.sizeof(api.FrameParams) * world, "d2h_bytes_per_step": work.height * work.width * 16,
+           "steps": n_e2e, "api": e2e_api}
+    if world > 1 and rank == 0:
+        e2e["host_frame_complete"] = work.e2e_check
 
-    # ---- roofline of the dominant kernel (k_render), measured live ---------------------------------
+    fp32_peak = l2_peak = hbm_peak = None
     roofline = None
     if rank == 0:
-        # work per ray from the counting build (one frame)
-        stats = torch.zeros((6,), dtype=torch.int64, device=dev)
-        def my_share(step):
-            q = params_for(step, 0, height)
-            if world > 1:
-                q.strip_stride, q.strip_offset = world, rank
-            return q
-
-        from raytracingdiffusioncurves_b200.distributed import STRIP as rd_strip
-
-        my_rows = sum(min(rd_strip, height - t * rd_strip) for t in range(rank, (height + rd_strip - 1) // rd_strip, world))
-        p = my_share(0)
-        p.stats = stats.data_ptr()
-        scene.render(p, band.data_ptr(), sigma_band.data_ptr(), stream)
-        torch.cuda.synchronize()
-        traced, nodes, chords, shaded, deferred, gathered = [float(x) for x in stats.cpu().tolist()]
-        nodes += gathered
-        band_rays = float(my_rows) * width * rpp
-        n_node, n_seg, n_hit = nodes / band_rays, chords / band_rays, shaded / band_rays
-        f_ray = F_GEN + n_node * F_NODE + n_seg * F_SEG + n_hit * F_SHADE + F_ACC
-        # the kernel alone, CUDA events on its stream
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(5, min(args.steps, 30))
-        pk = my_share(1)
-        pk.max_sigma = flag.data_ptr()
-        k0.record()
-        for _ in range(reps):
-            scene.render(pk, band.data_ptr(), sigma_band.data_ptr(), stream)
-        k1.record()
-        torch.cuda.synchronize()
-        kernel_ms = k0.elapsed_time(k1) / reps
-        # FP32 peak: dependent-FFMA microbenchmark on the same box, same moment
-        sink = torch.zeros((4,), dtype=torch.float32, device=dev)
-        flops = ctypes.c_double()
-        api.lib.rdc_microbench_fp32(2048, 2, sink.data_ptr(), ctypes.byref(flops), stream)
-        torch.cuda.synchronize()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        api.lib.rdc_microbench_fp32(2048, 10, sink.data_ptr(), ctypes.byref(flops), stream)
-        m1.record()
-        torch.cuda.synchronize()
-        fp32_peak = flops.value * 10 / (m0.elapsed_time(m1) * 1e-3) / 1e12
-        achieved = band_rays * f_ray / (kernel_ms * 1e-3) / 1e12
-        hbm_peak = None
+        fp32_peak, l2_peak = measure_peaks(api, torch, stream, dev)
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
                 hbm_peak = json.load(fh).get("hbm_gbs")
         except Exception:
             pass
-        alg_bytes = float(my_rows) * width * 20.0
-        roofline = {
-            "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp32_peak,
-            "traffic": NCU_CAPTURE.get(args.workload, {}).get("dram_bytes") if world == 1 else None,
-            "issue_slots": NCU_CAPTURE.get(args.workload) if world == 1 else None,
-            "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
-            "kernel_ms": kernel_ms, "flops_per_ray": f_ray,
-            "per_ray": {"nodes": n_node, "chords": n_seg, "hits_shaded": n_hit, "rays_traced": traced / band_rays,
-                        "deferred_to_tree": deferred / band_rays, "table_query_nodes": gathered / band_rays},
-            "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                    "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
-                    "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; the partial sums of split work "
-                            "units stay in L2 (their lines are discarded once added up, see DESIGN.md 3.1)"},
-        }
+        roofline = roofline_block(work, work.kernel_roofline(max(5, min(args.steps, 30))), fp32_peak, l2_peak, hbm_peak, world == 1)
+    details = {"curves": work.scene.stats.n_curves, "segments": work.scene.stats.n_segments, "chords": work.scene.stats.n_chords,
+               "runs": work.scene.stats.n_runs, "bvh_depth": work.scene.stats.bvh_depth, "exchange": work.exchange,
+               "setup_ms": {"ingest": work.ingest_ms, "upload_and_tree_build": work.build_ms},
+               "wall_ms_per_step_incl_flush": wall / args.steps * 1e3, "source_sha16": source_sha16()}
+    launches = work.launches_per_step * args.steps * world
+    kind = work.kind
+    work.close()
+
+    # ---- secondary: BASELINE.json configs[4], the 8192x8192 @512 synthetic 100 k-curve scene, a few frames at this N ----
+    secondary = None
+    if args.secondary and args.workload == DEFAULT_WORKLOAD:
+        sec = Workload("synth100k_8k_512rpp", api, torch, dist, dev, rank, world)
+        sec_ms, _ = sec.time_value(args.secondary_steps, 1, flush)
+        sec_rays = float(sec.width) * sec.height * sec.rpp
+        if rank == 0:
+            k = sec.kernel_roofline(2)
+            secondary = {"config": workload_config(sec.name, world), "metric": "Grays/s", "value": sec_rays / (sec_ms * 1e-3) / 1e9,
+                         "ms_per_step": sec_ms, "steps": args.secondary_steps, "warmup": 1, "n_gpus": world, "scaling": "strong",
+                         "chords": sec.scene.stats.n_chords, "runs": sec.scene.stats.n_runs,
+                         "setup_ms": {"ingest": sec.ingest_ms, "upload_and_tree_build": sec.build_ms},
+                         "roofline": roofline_block(sec, k, fp32_peak, l2_peak, hbm_peak, world == 1)}
+        launches += sec.launches_per_step * (args.secondary_steps + 1) * world
+        sec.close()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_oracle_run("reference", spec, width, height, rpp, depth, zoom, args.cpu_seconds)
+        spec, width, height, rpp, depth = WORKLOADS[args.workload]
+        cpu_baseline = cpu_oracle_run("reference", spec, width, height, rpp, depth, workload_zoom(spec, height), args.cpu_seconds)
 
     if rank == 0:
-        st = scene.stats
         line = {
             "metric": "Grays/s", "value": value, "unit": "Grays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "bundled scene file (tests/golden/xmls)" if kind == "file" else "synthetic (rdc_synth_xml, SplitMix64 0x5EEDC0DE)",
             "config": workload_config(args.workload, world),
-            "details": {"curves": st.n_curves, "segments": st.n_segments, "chords": st.n_chords, "runs": st.n_runs, "bvh_depth": st.bvh_depth,
-                        "exchange": exchange if world > 1 else None, "setup_ms": setup_ms,
-                        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+            "details": details,
             "clocks": sampler.result(),
             "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps * world,
+            "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -261,6 +261,10 @@ int rdc_write_png(const char* path, const uint8_t* rgba, int width, int height);
  * at glfw_events.cpp:94 — alpha ignored, and its out-of-range quality argument ends up as 100. quality 1..100. */
 int rdc_write_jpg(const char* path, const uint8_t* rgba, int width, int height, int quality);
 
+/* image-level comparison of two float4 host images, RGB only, NaN-aware (pixels that are NaN in both are skipped):
+ * PSNR in dB on the [0,1] scale and the largest absolute difference — what BASELINE.json asks to be reported */
+int rdc_psnr(const float* a, const float* b, size_t n_pixels, double* psnr, double* max_abs);
+
 /* ---- the steps either side of the path in the frame loop ---- */
 /* scroll_callback (glfw_events.cpp:105-112): zoom_factor *= 1.5^-yoffset */
 void rdc_view_scroll(rdc_frame_params* params, double yoffset);
@@ -279,6 +283,10 @@ int rdc_synth_xml(uint32_t n_curves, uint32_t width, uint32_t height, uint64_t s
  *      Launches `launches` kernels of 148*8 blocks x 256 threads, each thread doing iters*64 FFMAs, on
  *      `stream`; returns the flop count of ONE launch in *flops_per_launch. Enqueue-only. ---- */
 int rdc_microbench_fp32(int iters, int launches, float* sink, double* flops_per_launch, rdc_stream stream);
+/* L2-read microbenchmark (the L2-side denominator for scenes whose runs and tree live in L2): each launch reads `bytes`
+ * of `buffer` (device memory, small enough to stay in L2) `passes` times with 128-bit loads that bypass L1. */
+int rdc_microbench_l2(const void* buffer, size_t bytes, int passes, int launches, float* sink, double* bytes_per_launch,
+                      rdc_stream stream);
 
 const char* rdc_last_error_string(void);
 const char* rdc_version(void);

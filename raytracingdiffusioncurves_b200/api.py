@@ -126,11 +126,13 @@ PROTOTYPES = {
     "rdc_write_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "rdc_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "rdc_write_jpg": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "rdc_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rdc_view_scroll": (None, [C.POINTER(FrameParams), C.c_double]),
     "rdc_view_drag": (None, [C.POINTER(FrameParams), C.c_double, C.c_double]),
     "rdc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "rdc_synth_xml": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rdc_microbench_fp32": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "rdc_microbench_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "rdc_last_error_string": (C.c_char_p, []),
     "rdc_version": (C.c_char_p, []),
 }
@@ -483,6 +485,16 @@ def image_to_rgba8(image: np.ndarray, flip: bool) -> np.ndarray:
     return out
 
 
+def psnr(a: np.ndarray, b: np.ndarray) -> tuple[float, float]:
+    """rdc_psnr on two [H, W, 4] float images: (PSNR in dB, largest absolute RGB difference)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape and a.shape[-1] == 4
+    p, m = C.c_double(), C.c_double()
+    _check(_lib.rdc_psnr(a.ctypes.data, b.ctypes.data, a.size // 4, C.byref(p), C.byref(m)), "rdc_psnr")
+    return p.value, m.value
+
+
 def row_band(height: int, rank: int, world: int) -> tuple[int, int]:
     """Rows [begin,end) of rank `rank` of `world`: contiguous bands, remainder spread over the first ranks."""
     base, rem = divmod(height, world)
@@ -505,14 +517,3 @@ def cuda_callbacks(scene: "Scene", make_params, stream: int = 0):
                            row_begin, row_end, halo, 0, stream)
 
     return render_strips, blur_rows
-
-
-def cuda_peer_callbacks(scene: "Scene", make_params, stream: int = 0):
-    """(render_to, blur_rows) for distributed.render_frame_peer: the render stores straight into the target frames."""
-
-    def render_to(image_ptrs, sigma_ptrs, stride, offset):
-        p = make_params()
-        p.strip_stride, p.strip_offset = (stride, offset) if stride > 1 else (0, 0)
-        scene.render_to_frames(p, image_ptrs, sigma_ptrs, stream)
-
-    return render_to, cuda_callbacks(scene, make_params, stream)[1]

@@ -112,6 +112,15 @@ inline unsigned grid_for(size_t n) {
 
 }  // namespace
 
+// forces the blur kernels' module to load now (a later first launch would otherwise do it, and loading may have to
+// wait for the device to go idle — not something to meet between two barrier kernels)
+int blur_preload() {
+  cudaFuncAttributes fa;
+  RDC_CUDA(cudaFuncGetAttributes(&fa, k_blur_horizontal));
+  RDC_CUDA(cudaFuncGetAttributes(&fa, k_blur_vertical));
+  return 0;
+}
+
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
                   int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows) {
   if (!dest || !src || !sigma || !scratch || width <= 0 || height <= 0 || row_begin < 0 || row_end > height ||

@@ -128,6 +128,7 @@ int reserve(rdc_scene* s, const rdc_frame_params& p, cudaStream_t stream);
 int gaussian_blur(float4* dest, const float4* src, const float* sigma, float4* scratch, int width, int height,
                   int row_begin, int row_end, const float* max_sigma, cudaStream_t stream, int halo_rows = -1);
 int set_float(float* dest, unsigned n, float v, cudaStream_t stream);
+int blur_preload();
 }  // namespace rdc
 
 #define RDC_CUDA(call)                                            \

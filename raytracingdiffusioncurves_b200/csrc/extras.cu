@@ -63,6 +63,32 @@ void rdc_view_drag(rdc_frame_params* p, double dx, double dy) {
   p->offset_y -= dy * p->zoom_factor;
 }
 
+// Image-level comparison of two float4 images in host memory (the diff tool). RGB only; pixels
+// that are NaN (all rays missed, DeviceCode.cu:176-181) in BOTH images are skipped, NaN in one only counts as a
+// full-scale error. psnr = 10 log10(1 / mse) on the [0,1] scale (+inf when identical), max_abs = largest |difference|.
+int rdc_psnr(const float* a, const float* b, size_t n_pixels, double* psnr, double* max_abs) {
+  if (!a || !b || n_pixels == 0 || !psnr || !max_abs) {
+    rdc::set_error("psnr: bad argument");
+    return RDC_E_INVALID;
+  }
+  double sum = 0.0, worst = 0.0;
+  size_t counted = 0;
+  for (size_t i = 0; i < n_pixels; ++i)
+    for (int c = 0; c < 3; ++c) {
+      const float x = a[4 * i + c], y = b[4 * i + c];
+      const bool nx = x != x, ny = y != y;
+      if (nx && ny) continue;
+      const double d = (nx || ny) ? 1.0 : (double)x - (double)y;
+      sum += d * d;
+      if (std::fabs(d) > worst) worst = std::fabs(d);
+      counted++;
+    }
+  const double mse = counted ? sum / (double)counted : 0.0;
+  *psnr = mse == 0.0 ? INFINITY : 10.0 * std::log10(1.0 / mse);
+  *max_abs = worst;
+  return 0;
+}
+
 int rdc_accumulate(float* accum, const float* image, size_t n_pixels, uint32_t frames_so_far, rdc_stream stream) {
   if (!accum || !image || n_pixels == 0) {
     rdc::set_error("accumulate: bad argument");

@@ -36,7 +36,7 @@ struct rdc_peer_frames {
   float4* full_image = nullptr;   // the whole rendered frame (blur scenes: every rank's copy is filled)
   float* full_sigma = nullptr;    // + one float: the max-sigma flag of this rank's launches
   float4* frames[2] = {nullptr, nullptr};  // finished frames, used in turn (consumed on rank 0; the band blur's target elsewhere)
-  float4* scratch = nullptr;      // blur scratch, allocated on first use
+  float4* scratch = nullptr;      // blur scratch
   float4* packed[2] = {nullptr, nullptr};  // this rank's strips, packed (host path without blur), used in turn
   float* packed_sigma = nullptr;
   unsigned int* pads = nullptr;   // [world] arrival flags written by the peers, [world] = error flag
@@ -106,6 +106,8 @@ int free_local(rdc_peer_frames* f) {
 
 extern "C" {
 
+void rdc_peer_frames_destroy(rdc_peer_frames* f);
+
 int rdc_peer_frames_create(uint32_t width, uint32_t height, int rank, int world, rdc_peer_frames** out) {
   if (!out || width == 0 || height == 0 || world < 1 || world > RDC_MAX_FRAME_TARGETS || rank < 0 || rank >= world) {
     rdc::set_error("peer frames: bad argument (1 <= world <= %d, 0 <= rank < world)", RDC_MAX_FRAME_TARGETS);
@@ -125,6 +127,7 @@ int rdc_peer_frames_create(uint32_t width, uint32_t height, int rank, int world,
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->full_sigma, (n + 1) * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->frames[0], n * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->frames[1], n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&f->scratch, n * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->packed[0], packed_rows * width * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->packed[1], packed_rows * width * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc((void**)&f->packed_sigma, (packed_rows * width + 1) * sizeof(float));
@@ -146,6 +149,14 @@ int rdc_peer_frames_create(uint32_t width, uint32_t height, int rank, int world,
   f->peer_frames[1][rank] = f->frames[1];
   f->peer_pads[rank] = f->pads;
   f->connected = world == 1;
+  // load every kernel the frame loop launches now: a first launch in the middle of a frame would load its module then,
+  // which may wait for the device to go idle — while a barrier kernel of this very frame is spinning on it
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, rdc::k_peer_barrier);
+  if (e != cudaSuccess || rdc::blur_preload() != 0) {
+    rdc_peer_frames_destroy(f);
+    return e != cudaSuccess ? rdc::cuda_fail(e, "peer frames: kernel load") : RDC_E_INVALID;
+  }
   *out = f;
   return 0;
 }
@@ -329,7 +340,6 @@ int rdc_peer_render_frame(rdc_scene* scene, rdc_peer_frames* f, const rdc_frame_
   if (int rc = rdc::render(scene, p, nullptr, nullptr, st, (uint32_t)f->world, images, sigmas)) return rc;  // the all-gather
   if (wait_event) RDC_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)wait_event, 0));
   if (int rc = rdc_peer_barrier(f, stream)) return rc;
-  if (!f->scratch) RDC_CUDA(cudaMalloc((void**)&f->scratch, (size_t)f->width * f->height * sizeof(float4)));
   // contiguous band of this rank, remainder rows spread over the first ranks
   const int base = (int)f->height / f->world, rem = (int)f->height % f->world;
   const int b = f->rank * base + (f->rank < rem ? f->rank : rem), e = b + base + (f->rank < rem ? 1 : 0);
@@ -402,7 +412,6 @@ int rdc_peer_frame_to_host(rdc_scene* scene, rdc_peer_frames* f, const rdc_frame
   // full_image of a rank is read by its band blur and overwritten by every rank's next render: a closing barrier per frame
   if (int rc = rdc::render(scene, p, nullptr, nullptr, st, (uint32_t)f->world, images, sigmas)) return rc;
   if (int rc = rdc_peer_barrier(f, stream)) return rc;
-  if (!f->scratch) RDC_CUDA(cudaMalloc((void**)&f->scratch, (size_t)f->width * f->height * sizeof(float4)));
   const int base = (int)f->height / f->world, rem = (int)f->height % f->world;
   const int b = f->rank * base + (f->rank < rem ? f->rank : rem), e = b + base + (f->rank < rem ? 1 : 0);
   RDC_CUDA(cudaStreamWaitEvent(st, f->copied[slot], 0));

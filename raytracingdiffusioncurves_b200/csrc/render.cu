@@ -1272,6 +1272,48 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   return L;
 }
 
+// The kernel of a plan's variant; on first use per handle: dynamic shared memory limit and the SM-filling grid size
+// (which also forces the kernel's module to load — rdc_scene_reserve calls this so that no later launch has to).
+typedef void (*RenderKernel)(RenderArgs);
+int prepare_variant(rdc_scene* s, const LaunchPlan& L, RenderKernel* out) {
+  const int variant = L.variant;
+  const size_t dyn = L.dyn;
+  RenderKernel kernel = nullptr;
+  switch (variant) {
+    case 0: kernel = k_render<false, false, false, kModeTree>; break;
+    case 1: kernel = k_render<true, false, false, kModeTree>; break;
+    case 2: kernel = k_render<false, true, false, kModeTree>; break;
+    case 3: kernel = k_render<true, true, false, kModeTree>; break;
+    case 6: kernel = k_render<false, true, true, kModeTree>; break;
+    case 7: kernel = k_render<true, true, true, kModeTree>; break;
+    case 9: kernel = k_render<true, false, false, kModeTable>; break;
+    case 11: kernel = k_render<true, true, false, kModeTable>; break;
+    case 15: kernel = k_render<true, true, true, kModeTable>; break;
+    case 16: kernel = k_render<false, false, false, kModeLocal>; break;
+    case 17: kernel = k_render<true, false, false, kModeLocal>; break;
+    case 18: kernel = k_render<false, true, false, kModeLocal>; break;
+    case 19: kernel = k_render<true, true, false, kModeLocal>; break;
+    case 22: kernel = k_render<false, true, true, kModeLocal>; break;
+    case 23: kernel = k_render<true, true, true, kModeLocal>; break;
+    default:
+      set_error("render: no kernel variant %d", variant);
+      return RDC_E_INVALID;
+  }
+  if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
+    if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int per_sm = 0, sms = 0;
+    RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
+    RDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (per_sm < 1 || sms < 1) {
+      set_error("render: the kernel does not fit an SM");
+      return RDC_E_LIMIT;
+    }
+    s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
+  }
+  *out = kernel;
+  return 0;
+}
+
 // Scratch a launch of this plan needs; grows only. Allocating means a device-wide synchronisation (cudaFree), which
 // is why rdc_scene_reserve exists.
 int ensure_capacity(rdc_scene* s, const LaunchPlan& L, cudaStream_t stream) {
@@ -1312,6 +1354,11 @@ int reserve(rdc_scene* s, const rdc_frame_params& p, cudaStream_t stream) {
   // the widest plan the parameters can lead to: the counting build and both routes share the same scratch sizes
   const LaunchPlan L = plan_launch(s, p);
   if (L.local_rows == 0) return 0;
+  RenderKernel kernel = nullptr;
+  if (int rc = prepare_variant(s, L, &kernel)) return rc;
+  cudaFuncAttributes fa;
+  RDC_CUDA(cudaFuncGetAttributes(&fa, k_base_dirs));
+  if (!s->launched) RDC_CUDA(cudaEventCreateWithFlags(&s->launched, cudaEventDisableTiming));
   return ensure_capacity(s, L, stream);
 }
 
@@ -1385,40 +1432,10 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   a.row_skew = L.row_skew;
   a.local_r0 = L.local_r0;
   a.work = s->work_counters;
+  void (*kernel)(RenderArgs) = nullptr;
+  if (int rc = prepare_variant(s, L, &kernel)) return rc;
   const int variant = L.variant;
   const size_t dyn = L.dyn;
-  void (*kernel)(RenderArgs) = nullptr;
-  switch (variant) {
-    case 0: kernel = k_render<false, false, false, kModeTree>; break;
-    case 1: kernel = k_render<true, false, false, kModeTree>; break;
-    case 2: kernel = k_render<false, true, false, kModeTree>; break;
-    case 3: kernel = k_render<true, true, false, kModeTree>; break;
-    case 6: kernel = k_render<false, true, true, kModeTree>; break;
-    case 7: kernel = k_render<true, true, true, kModeTree>; break;
-    case 9: kernel = k_render<true, false, false, kModeTable>; break;
-    case 11: kernel = k_render<true, true, false, kModeTable>; break;
-    case 15: kernel = k_render<true, true, true, kModeTable>; break;
-    case 16: kernel = k_render<false, false, false, kModeLocal>; break;
-    case 17: kernel = k_render<true, false, false, kModeLocal>; break;
-    case 18: kernel = k_render<false, true, false, kModeLocal>; break;
-    case 19: kernel = k_render<true, true, false, kModeLocal>; break;
-    case 22: kernel = k_render<false, true, true, kModeLocal>; break;
-    case 23: kernel = k_render<true, true, true, kModeLocal>; break;
-    default:
-      set_error("render: no kernel variant %d", variant);
-      return RDC_E_INVALID;
-  }
-  if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
-    if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    int per_sm = 0, sms = 0;
-    RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
-    RDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    if (per_sm < 1 || sms < 1) {
-      set_error("render: the kernel does not fit an SM");
-      return RDC_E_LIMIT;
-    }
-    s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
-  }
   a.split = L.split;
   a.part_rgbw = s->part_rgbw;
   a.part_blur = s->part_blur;

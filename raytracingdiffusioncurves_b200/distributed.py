@@ -19,12 +19,14 @@ The data path has at most two exchange steps:
                   ceil(3*sigma_max) rows the vertical pass can reach, helperKernels.cu:65,74);
       gather      blurred bands -> rank 0
 
-On GPUs the default is the peer-memory form of the same plan (PeerFrameBuffers / render_frame_peer): the frame
-buffers are symmetric memory (every rank holds the device address of every other rank's buffer, NVLink peer
-access), and the render kernel stores each finished pixel straight into its place in the consumer's frame —
-rank 0's when the scene has no blur, everybody's when it has (the all-gather) — and the band blur stores straight
-into rank 0's finished frame. The stores ARE the collectives; what is left is one barrier over the ranks'
-streams per exchange step. The NCCL form above stays as the fallback and is what the gloo CPU tests exercise.
+On GPUs the product path is the peer-memory form of the same plan, and it is NOT in this module: it is C++ behind
+the C ABI (csrc/peer.cu — rdc_peer_frames_*, rdc_peer_render_frame, rdc_peer_frame_to_host; api.PeerFrames marshals the
+pointers). Every rank holds the device address of every other rank's frame buffers (CUDA IPC or peer access), the
+render kernel stores each finished pixel straight into its place in the consumer's frame — rank 0's when the scene has
+no blur, everybody's when it has (the all-gather) — and the band blur stores straight into rank 0's finished frame. The
+stores ARE the collectives; what is left is one barrier kernel per exchange step. `render_frame_peer` below is the
+executable statement of that protocol (which buffer, which barrier, in which order) that the gloo CPU tests run with
+shared host memory standing in for peer memory; `render_frame` is the collective form (NCCL / gloo) of the same plan.
 
 What renders and what blurs is injected (`render_strips`, `blur_rows`): the product passes the CUDA entry
 points (api.cuda_callbacks), the CPU tests pass the oracle. This module only moves rows.
@@ -155,48 +157,7 @@ def render_frame(buf: FrameBuffers, render_strips, blur_rows, use_blur: bool = T
     return buf.frame
 
 
-class PeerFrameBuffers:
-    """Symmetric-memory frame buffers for render_frame_peer (GPUs of one box, NVLink peer access).
-
-    `full_image` / `full_sigma` hold the whole rendered frame (every rank has one; without blur only rank 0's
-    sigma is written), `frames` two finished frames used in turn (meaningful on rank 0) so that rank 0 can still be
-    copying frame f out while frame f+1 is rendered into the other. Raises if symmetric memory is not available —
-    the caller then stays on FrameBuffers / render_frame."""
-
-    def __init__(self, plan: StripPlan, device, group=None):
-        import torch.distributed._symmetric_memory as symm
-
-        p = self.plan = plan
-        group = group if group is not None else dist.group.WORLD
-        f32 = dict(dtype=torch.float32, device=device)
-        # Allocation is local and may fail on one rank only; the rendezvous below is collective. Agree first, so
-        # that no rank waits in a rendezvous the others never enter.
-        error = None
-        try:
-            self.full_image = symm.empty((p.height, p.width, 4), **f32)
-            self.full_sigma = symm.empty((p.height, p.width), **f32)
-            self.frames = [symm.empty((p.height, p.width, 4), **f32) for _ in range(2)]
-        except Exception as exc:  # noqa: BLE001
-            error = exc
-        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
-            raise RuntimeError(f"symmetric memory could not be allocated on every rank ({error!r} here)")
-        self.h_image = symm.rendezvous(self.full_image, group)
-        self.h_sigma = symm.rendezvous(self.full_sigma, group)
-        self.h_frames = [symm.rendezvous(f, group) for f in self.frames]
-        self.image_ptrs = [int(x) for x in self.h_image.buffer_ptrs]
-        self.sigma_ptrs = [int(x) for x in self.h_sigma.buffer_ptrs]
-        self.frame_ptrs = [[int(x) for x in h.buffer_ptrs] for h in self.h_frames]
-        self.scratch = torch.zeros((p.height, p.width, 4), **f32) if p.halo > 0 else None
-        self.turn = 0
-
-    def barrier(self):
-        """All ranks' streams meet: what was enqueued before it on any rank is complete and visible after it."""
-        self.h_image.barrier()
-
-
-def render_frame_peer(buf: PeerFrameBuffers, render_to, blur_rows, use_blur: bool = True, before_barrier=None):
+def render_frame_peer(buf, render_to, blur_rows, use_blur: bool = True, before_barrier=None):
     """One frame over all ranks through peer memory. Returns the finished frame [H, W, 4] on rank 0, None elsewhere.
 
     render_to(image_ptrs, sigma_ptrs, stride, offset): renders strips t % stride == offset and stores every pixel
