@@ -118,7 +118,7 @@ void rdc_scene_destroy(rdc_scene* scene);
 #define RDC_ROUTE_AUTO 0        /* whole-scene run table up to 64 runs, per-tile local run table for large scenes
                                    seen closely enough, the tree otherwise                                    */
 #define RDC_ROUTE_TREE 1        /* always the LBVH                                                            */
-#define RDC_ROUTE_LOCAL_TABLE 2 /* per-tile local run table whenever the scene has more than 64 runs          */
+#define RDC_ROUTE_LOCAL_TABLE 2 /* per-tile local run table whatever the size of the scene                     */
 
 typedef struct rdc_frame_params {
   uint32_t image_width, image_height;   /* output size (params.h:48-49)                               */

@@ -28,6 +28,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(HERE, "_build", "liboracle_port.so")
 REF_LIB = os.path.join(HERE, "_ref", "libref_oracle.so")
 REF_XML_DUMP = os.path.join(HERE, "_ref", "ref_xml_dump")
+REF_INGEST_LIB = os.path.join(HERE, "_ref", "libref_ingest.so")
+REF_BLUR_LIB = os.path.join(HERE, "_ref", "libref_blur.so")
 
 f32 = np.float32
 
@@ -449,6 +451,57 @@ class Oracle:
         out = np.empty_like(src)
         self.lib.oracle_blur(out.ctypes.data, src.ctypes.data, sig.ctypes.data, w, h, threads)
         return out
+
+
+def ref_ingest(path: str) -> dict:
+    """The reference's OWN ingest loop (optixHello.cpp:108-117,170-515 and helpers :1302-1386, cut out and compiled for the
+    host by oracle/ref_extract.sh) run on `path`. Same dictionary layout as ingest_xml, WITHOUT the +INF sentinels the
+    product appends (the reference has none). Compiled with the reference's USE_DIFFUSION_CURVE_SAVE (true)."""
+    lib = C.CDLL(REF_INGEST_LIB)
+    lib.ref_ingest.argtypes = [C.c_char_p]
+    lib.ref_ingest_array.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.ref_ingest_array.restype = C.c_void_p
+    if lib.ref_ingest(os.fsencode(path)) != 0:
+        raise RuntimeError(f"the reference's ingest failed on {path}")
+
+    def arr(name, dtype, cols):
+        n, eb = C.c_size_t(), C.c_size_t()
+        ptr = lib.ref_ingest_array(name.encode(), C.byref(n), C.byref(eb))
+        assert n.value != 2 ** 64 - 1, name
+        if n.value == 0:
+            return np.zeros((0, cols) if cols > 1 else (0,), dtype)
+        flat = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value * eb.value,)).copy().view(dtype)
+        return flat.reshape(n.value, cols) if cols > 1 else flat
+
+    w, h = C.c_int(), C.c_int()
+    lib.ref_ingest_size(C.byref(w), C.byref(h))
+    out = {"image_width": w.value, "image_height": h.value, "vertices": arr("vertices", np.float32, 3),
+           "segment_indices": arr("segmentIndices", np.uint32, 1), "curve_map": arr("curve_map", np.uint32, 1),
+           "curve_index": arr("curve_index", np.uint32, 1), "curve_connect": arr("curve_connect", np.int32, 1),
+           "curve_map_inverse": arr("curve_map_inverse", np.uint32, 1)}
+    for fam in ("color_left", "color_right", "blur", "weight", "weight_degree"):
+        out[fam + "_index"] = arr(fam + "_index", np.uint32, 2)
+        out[fam] = arr(fam, np.float32, 3 if fam.startswith("color") else 1)
+        out[fam + "_u"] = arr(fam + "_u", np.float32, 1)
+        out["n_" + fam] = len(out[fam + "_u"])
+    return out
+
+
+def ref_blur(image: np.ndarray, sigma: np.ndarray, threads: int = 0) -> np.ndarray:
+    """The reference's OWN gaussHorizontal / gaussVertical (helperKernels.cu:48-134, cut out and compiled for the host by
+    oracle/ref_extract.sh), through the launcher sequence of :137-148."""
+    lib = C.CDLL(REF_BLUR_LIB)
+    lib.ref_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h, w, _ = image.shape
+    src = np.ascontiguousarray(image, np.float32)
+    sig = np.ascontiguousarray(sigma, np.float32)
+    out = np.empty_like(src)
+    lib.ref_blur(out.ctypes.data, src.ctypes.data, sig.ctypes.data, w, h, threads)
+    return out
+
+
+def ref_extracts_available() -> bool:
+    return os.path.exists(REF_INGEST_LIB) and os.path.exists(REF_BLUR_LIB)
 
 
 def ref_xml_dump(path: str) -> str:

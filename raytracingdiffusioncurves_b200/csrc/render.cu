@@ -131,6 +131,32 @@ __device__ __forceinline__ float slab_rcp(float d) {
   return r;
 }
 
+// Slab test of a padded box in fused form: t = x * (1/d) - o * (1/d), the second product computed once per ray.
+// Culling only — never decides a hit: against rdc_slab the entry and exit distances move by a few ulp of |o / d|, i.e. the
+// box is displaced by ~1e-7 of the origin's coordinates, which the boxes' padding (curve_width + 4e-6 x scene extent,
+// accel.cu) covers forty times over. Halves the adds of the test (16 -> 12 operations per box).
+struct SlabRay {
+  float idx, idy, nox, noy;  // 1/dx, 1/dy, -ox/dx, -oy/dy
+};
+__device__ __forceinline__ SlabRay slab_ray(float ox, float oy, float dx, float dy) {
+  SlabRay r;
+  r.idx = slab_rcp(dx);
+  r.idy = slab_rcp(dy);
+  r.nox = -(ox * r.idx);
+  r.noy = -(oy * r.idy);
+  return r;
+}
+__device__ __forceinline__ float slab_enter(const SlabRay& r, float ox, float oy, float4 b, float* exit) {
+#ifdef RDC_SLAB_FMA
+  const float tx1 = fmaf(b.x, r.idx, r.nox), tx2 = fmaf(b.z, r.idx, r.nox);
+  const float ty1 = fmaf(b.y, r.idy, r.noy), ty2 = fmaf(b.w, r.idy, r.noy);
+  *exit = fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2));
+  return fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), 0.0f);
+#else
+  return rdc_slab(ox, oy, r.idx, r.idy, b.x, b.y, b.z, b.w, exit);
+#endif
+}
+
 // All chords of one run against the ray. Edge values of the shared end points are computed once; the
 // record is read two points at a time and only as far as the run is long. The unrolled pass only marks
 // the chords whose end points lie on different sides of the ray; the (rare) marked ones are then resolved
@@ -223,7 +249,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
 #pragma unroll
   for (int k = 0; k < W; ++k) rest |= m[k];
   if (rest != 0u) {
-    const float idx = slab_rcp(dx), idy = slab_rcp(dy);
+    const SlabRay sr = slab_ray(ox, oy, dx, dy);
     bool open = true;  // local table: slots come in order of distance — once one lies beyond the hit, all the rest do
 #pragma unroll 1
     for (int w = 0; w < W && (!LOCAL || open); ++w) {
@@ -237,7 +263,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
         }
         const float4 b = LOCAL ? wl->box[slot] : ac.run_box[slot];
         float te;
-        const float tn = rdc_slab(ox, oy, idx, idy, b.x, b.y, b.z, b.w, &te);
+        const float tn = slab_enter(sr, ox, oy, b, &te);
         if (STATS) cnt.nodes++;
         if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
           const int run = LOCAL ? (int)wl->run[slot] : slot;
@@ -278,10 +304,59 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
     if (STATS) cnt.chords += ac.n_runs * RDC_RUN;  // upper bound
     return h;
   }
-  const float idx = slab_rcp(dx), idy = slab_rcp(dy);
+  const SlabRay sr = slab_ray(ox, oy, dx, dy);
   int2 stack[kStack];  // (node, entry distance bits)
   int sp = 0;
   int node = 0;
+#ifdef RDC_WHILE_WHILE
+  // while-while form (Aila & Laine 2009): every lane first walks inner nodes until it stands on a leaf (or has nothing
+  // left), then the warp tests leaves together — a lane on a leaf no longer waits out its neighbours' node steps one
+  // iteration at a time, and vice versa. Same visits in the same order per lane as the single loop below: same bits.
+  constexpr int kDone = 0x7fffffff;
+  for (;;) {
+    while (node >= 0 && node != kDone) {
+      if (STATS) cnt.nodes++;
+      const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
+      const float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
+      const float4 ch = load16<SMEM>(np + 2);
+      const int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+      float le, re;
+      const float ln = slab_enter(sr, ox, oy, lb, &le);
+      const float rn = slab_enter(sr, ox, oy, rb, &re);
+      const float lim = h.t * RDC_CULL_SLACK;
+      const bool hl = ln <= le && ln <= lim;
+      const bool hr = rn <= re && rn <= lim;
+      if (hl && hr) {
+        const bool left_first = ln <= rn;
+        stack[sp++] = make_int2(left_first ? right : left, __float_as_int(left_first ? rn : ln));
+        node = left_first ? left : right;
+      } else if (hl || hr) {
+        node = hl ? left : right;
+      } else {
+        node = kDone;
+        while (sp > 0) {  // the nearest pending subtree that still starts before the best hit
+          const int2 e = stack[--sp];
+          if (__int_as_float(e.y) <= lim) {
+            node = e.x;
+            break;
+          }
+        }
+      }
+    }
+    if (node == kDone) return h;
+    const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)(~node) * kRunVec, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
+    if (STATS) cnt.chords += looked;
+    node = kDone;
+    while (sp > 0) {
+      const int2 e = stack[--sp];
+      if (__int_as_float(e.y) <= h.t * RDC_CULL_SLACK) {
+        node = e.x;
+        break;
+      }
+    }
+    if (node == kDone) return h;
+  }
+#else
   for (;;) {
     if (node < 0) {
       const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)(~node) * kRunVec, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
@@ -293,8 +368,8 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
       const float4 ch = load16<SMEM>(np + 2);
       const int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
       float le, re;
-      const float ln = rdc_slab(ox, oy, idx, idy, lb.x, lb.y, lb.z, lb.w, &le);
-      const float rn = rdc_slab(ox, oy, idx, idy, rb.x, rb.y, rb.z, rb.w, &re);
+      const float ln = slab_enter(sr, ox, oy, lb, &le);
+      const float rn = slab_enter(sr, ox, oy, rb, &re);
       const float lim = h.t * RDC_CULL_SLACK;
       const bool hl = ln <= le && ln <= lim;
       const bool hr = rn <= re && rn <= lim;
@@ -319,6 +394,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
       }
     }
   }
+#endif
 }
 
 __device__ __forceinline__ void load_control_points(const DevScene& sc, uint32_t seg, rdc_f2 v[4]) {
@@ -1231,14 +1307,14 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
   const bool masks_ok = (float)L.n_iter == p.number_of_rays_per_pixel && L.n_iter >= 8 && !brute && p.route != RDC_ROUTE_TREE;
   //  * the whole scene in one table: at most 64 runs;
-  L.table = masks_ok && L.smem && s->dev.n_runs <= kTableRuns;
+  L.table = masks_ok && L.smem && s->dev.n_runs <= kTableRuns && p.route != RDC_ROUTE_LOCAL_TABLE;
   //  * a table per tile of the runs around it: larger scenes, unless the view is zoomed out so far that a tile's
   //    own footprint already meets more runs than the table holds. First radius: the one at which a scene of
   //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
   //    mean run box w x h; the kernel adapts it per tile.
   // measured on the bundled scenes: below 1024 runs the tree is as fast or faster (RDC_ROUTE_LOCAL_TABLE overrides)
-  const uint32_t local_min_runs = p.route == RDC_ROUTE_LOCAL_TABLE ? kTableRuns + 1 : 1024;
-  if (masks_ok && !L.table && s->dev.n_runs >= local_min_runs && s->dev.n_runs > kTableRuns) {
+  const uint32_t local_min_runs = p.route == RDC_ROUTE_LOCAL_TABLE ? 1 : 1024;
+  if (masks_ok && !L.table && s->dev.n_runs >= local_min_runs) {
     const float4 rb = s->dev.root_box;
     const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
     const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;

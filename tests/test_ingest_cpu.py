@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import all_scene_files, assert_scene_equal, scene_ids, XML_DIR
+from helpers import all_scene_files, assert_scene_equal, bits, scene_ids, XML_DIR
 from oracle import pyoracle as po
 from raytracingdiffusioncurves_b200 import api
 
@@ -184,3 +184,26 @@ def test_numbers_are_read_like_atof(tmp_path):
     bezier = [(v[0] + 4 * v[1] + v[2]) / 6, (2 * v[1] + v[2]) / 3, (v[1] + 2 * v[2]) / 3, (v[1] + 4 * v[2] + v[3]) / 6]
     np.testing.assert_allclose(bezier, want, atol=2e-5)
     assert s["blur"][:2].tolist() == [1.5, 2.25] and s["blur_u"][:2].tolist() == [0.0, 1.0]
+
+
+@pytest.mark.parametrize("path", all_scene_files(), ids=scene_ids())
+def test_product_ingest_equals_the_reference_own_loop(path):
+    """a2 pinned by the reference's code: optixHello.cpp:108-117,170-515 and its helpers :1302-1386, cut out of the file where
+    it lies and compiled for the host (oracle/ref_extract.sh -> oracle/_ref/libref_ingest.so), run on every bundled XML.
+    The product's arrays equal the reference's bit for bit (the product appends +INF sentinels after them)."""
+    from oracle import pyoracle as po
+
+    if not po.ref_extracts_available():
+        pytest.skip("oracle/_ref/libref_ingest.so not built (needs /root/reference at build time)")
+    ref = po.ref_ingest(path)
+    mine = api.HostScene.from_xml_file(path).to_numpy()
+    assert set(ref) == set(mine)
+    for k, v in ref.items():
+        if isinstance(v, np.ndarray):
+            m = np.ascontiguousarray(mine[k][: len(v)])
+            assert m.shape == v.shape, k
+            assert np.array_equal(bits(m), bits(np.ascontiguousarray(v))), k
+            if k.endswith("_u"):  # what follows the reference's entries is the two sentinels, nothing else
+                assert np.all(np.isinf(mine[k][len(v):])) and len(mine[k]) >= len(v) + 2
+        else:
+            assert mine[k] == v, k

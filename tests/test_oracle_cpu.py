@@ -146,3 +146,20 @@ def test_grid_search_equals_brute_force_reference_build(xml_dir, ref_oracle):
     a = ref_oracle.render(scene, p, want_hits=True, search="brute")
     b = ref_oracle.render(scene, p, want_hits=True, search="grid")
     assert np.array_equal(a[2], b[2]) and np.array_equal(bits(a[0]), bits(b[0]))
+
+
+def test_port_blur_equals_the_reference_own_kernels():
+    """a12 pinned by the reference's code: gaussHorizontal / gaussVertical (helperKernels.cu:48-134) cut out of the file and
+    compiled for the host (oracle/ref_extract.sh); the restated blur equals them bit for bit, sigma 0 and NaN included."""
+    if not po.ref_extracts_available():
+        pytest.skip("oracle/_ref/libref_blur.so not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(5)
+    image = rng.random((37, 53, 4), dtype=np.float32)
+    sigma = (rng.random((37, 53), dtype=np.float32) * 6.0).astype(np.float32)
+    sigma[sigma < 1.5] = 0.0
+    image[3, 4, :3] = np.nan  # an all-miss pixel (DeviceCode.cu:176-181) spreads like in the reference
+    want = po.ref_blur(image, sigma, threads=3)
+    got = po.Oracle("port").blur(image, sigma, threads=2)
+    assert np.array_equal(bits(got), bits(want))
+    big = po.ref_blur(image, np.full_like(sigma, 16.0))
+    assert np.array_equal(bits(po.Oracle("port").blur(image, np.full_like(sigma, 16.0))), bits(big))

@@ -230,6 +230,22 @@ def test_blur_parity(name, xml_dir, api, port_oracle):
     assert np.max(np.abs(got[m] - full[m]), initial=0) <= 2e-4
 
 
+def test_blur_against_the_reference_own_kernels(xml_dir, api):
+    """k_blur_* against gaussHorizontal / gaussVertical themselves (helperKernels.cu:48-134 compiled for the host by
+    oracle/ref_extract.sh), on a rendered frame with the scene's real sigmas."""
+    if not po.ref_extracts_available():
+        pytest.skip("oracle/_ref/libref_blur.so did not travel with the snapshot")
+    r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/fille.xml"))
+    w, h, n = 200, 150, 8
+    out = r.render(api.default_frame_params(w, h, n, zoom_factor=512 / h), blur=True)
+    assert out["max_sigma"] > 4.0
+    want = po.ref_blur(out["image"], out["blur_map"])[..., :3]
+    got = out["blurred"][..., :3]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.max(np.abs(got[m] - want[m]), initial=0) <= 1e-5
+
+
 def test_banded_blur_equals_full_blur(api):
     """rdc_gaussian_blur_band: horizontal pass only on the band plus the rows its vertical pass can reach."""
     import torch

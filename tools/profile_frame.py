@@ -29,6 +29,7 @@ def main():
     if os.environ.get("RDC_PROFILE_ROWS"):
         row_begin, row_end = (int(v) for v in os.environ["RDC_PROFILE_ROWS"].split(":"))
     rows = row_end - row_begin
+    route = int(os.environ.get("RDC_PROFILE_ROUTE", "0"))  # api.ROUTE_*: 0 automatic, 1 tree, 2 local run table
     image = torch.empty((rows, width, 4), dtype=torch.float32, device="cuda")
     sigma = torch.empty((rows, width), dtype=torch.float32, device="cuda")
     scratch = torch.empty_like(image)
@@ -37,7 +38,7 @@ def main():
     for f in range(frames):
         flag.zero_()
         p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=f, row_begin=row_begin,
-                                     row_end=row_end)
+                                     row_end=row_end, route=route)
         p.max_sigma = flag.data_ptr()
         t0.record()
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
@@ -52,7 +53,7 @@ def main():
     if os.environ.get("RDC_PROFILE_STATS"):
         stats = torch.zeros((6,), dtype=torch.int64, device="cuda")
         p = api.default_frame_params(width, height, rpp, zoom_factor=zoom, max_trace_depth=depth, frame=0, row_begin=row_begin,
-                                     row_end=row_end)
+                                     row_end=row_end, route=route)
         p.stats = stats.data_ptr()
         scene.render(p, image.data_ptr(), sigma.data_ptr(), stream)
         torch.cuda.synchronize()
