@@ -501,9 +501,11 @@ def roofline_block(work, k, fp32_peak, l2_peak, hbm_peak, single_gpu):
         "issue_slots": cap,
         "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
         "kernel_ms": k["kernel_ms"], "flops_per_ray": k["flops_per_ray"], "per_ray": k["per_ray"],
-        "l2": {"bytes_per_ray": k["l2_bytes_per_ray"], "achieved_gbs": l2_achieved, "peak_gbs": l2_peak, "frac": l2_achieved / l2_peak,
+        "l2": {"applies": work.scene.stats.traversal_bytes > 56 * 1024,  # smaller scenes are staged in shared memory: no L2 traffic to bound
+               "bytes_per_ray": k["l2_bytes_per_ray"], "achieved_gbs": l2_achieved, "peak_gbs": l2_peak, "frac": l2_achieved / l2_peak,
                "peak_source": "L2-read microbenchmark (rdc_microbench_l2: 32 MB buffer, ld.global.cg, 128-bit loads) run in this process",
-               "note": "SURVEY.md 8d: rays * (boxes + chords) * 32 B / t / L2 peak; the larger of the fp32 and l2 fractions is the binding one"},
+               "note": "SURVEY.md 8d: rays * (boxes + chords) * 32 B / t / L2 peak; the larger of the fp32 and l2 fractions is the binding one. "
+                       "An upper bound of the real L2 traffic: table slots' boxes come from shared memory and L1 serves part of the run records"},
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k["kernel_ms"] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": (alg_bytes / (k["kernel_ms"] * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                 "note": "output only (16 B image + 4 B sigma per pixel): the path is not HBM-bound; the partial sums of split work "

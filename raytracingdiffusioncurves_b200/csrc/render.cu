@@ -134,7 +134,8 @@ __device__ __forceinline__ float slab_rcp(float d) {
 // Slab test of a padded box in fused form: t = x * (1/d) - o * (1/d), the second product computed once per ray.
 // Culling only — never decides a hit: against rdc_slab the entry and exit distances move by a few ulp of |o / d|, i.e. the
 // box is displaced by ~1e-7 of the origin's coordinates, which the boxes' padding (curve_width + 4e-6 x scene extent,
-// accel.cu) covers forty times over. Halves the adds of the test (16 -> 12 operations per box).
+// accel.cu) covers forty times over. 12 operations per box instead of 16: lady_bug.xml 1080p 8.92 -> 8.49 ms, the 21-scene
+// 4K sweep 834 -> 805 ms (profiles/r02b/variants.log).
 struct SlabRay {
   float idx, idy, nox, noy;  // 1/dx, 1/dy, -ox/dx, -oy/dy
 };
@@ -146,15 +147,11 @@ __device__ __forceinline__ SlabRay slab_ray(float ox, float oy, float dx, float 
   r.noy = -(oy * r.idy);
   return r;
 }
-__device__ __forceinline__ float slab_enter(const SlabRay& r, float ox, float oy, float4 b, float* exit) {
-#ifdef RDC_SLAB_FMA
+__device__ __forceinline__ float slab_enter(const SlabRay& r, float4 b, float* exit) {
   const float tx1 = fmaf(b.x, r.idx, r.nox), tx2 = fmaf(b.z, r.idx, r.nox);
   const float ty1 = fmaf(b.y, r.idy, r.noy), ty2 = fmaf(b.w, r.idy, r.noy);
   *exit = fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2));
   return fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), 0.0f);
-#else
-  return rdc_slab(ox, oy, r.idx, r.idy, b.x, b.y, b.z, b.w, exit);
-#endif
 }
 
 // All chords of one run against the ray. Edge values of the shared end points are computed once; the
@@ -263,7 +260,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const WarpLocal* w
         }
         const float4 b = LOCAL ? wl->box[slot] : ac.run_box[slot];
         float te;
-        const float tn = slab_enter(sr, ox, oy, b, &te);
+        const float tn = slab_enter(sr, b, &te);
         if (STATS) cnt.nodes++;
         if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
           const int run = LOCAL ? (int)wl->run[slot] : slot;
@@ -308,10 +305,11 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   int2 stack[kStack];  // (node, entry distance bits)
   int sp = 0;
   int node = 0;
-#ifdef RDC_WHILE_WHILE
   // while-while form (Aila & Laine 2009): every lane first walks inner nodes until it stands on a leaf (or has nothing
   // left), then the warp tests leaves together — a lane on a leaf no longer waits out its neighbours' node steps one
-  // iteration at a time, and vice versa. Same visits in the same order per lane as the single loop below: same bits.
+  // iteration at a time, and vice versa. Same visits in the same order per lane as the single if/else loop it replaces:
+  // same bits; lady_bug.xml 1080p 8.49 -> 7.70 ms, dolphin.xml 4K 114.5 -> 109.4 ms on top of the fused slab test
+  // (profiles/r02b/variants.log).
   constexpr int kDone = 0x7fffffff;
   for (;;) {
     while (node >= 0 && node != kDone) {
@@ -321,8 +319,8 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
       const float4 ch = load16<SMEM>(np + 2);
       const int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
       float le, re;
-      const float ln = slab_enter(sr, ox, oy, lb, &le);
-      const float rn = slab_enter(sr, ox, oy, rb, &re);
+      const float ln = slab_enter(sr, lb, &le);
+      const float rn = slab_enter(sr, rb, &re);
       const float lim = h.t * RDC_CULL_SLACK;
       const bool hl = ln <= le && ln <= lim;
       const bool hr = rn <= re && rn <= lim;
@@ -356,45 +354,6 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
     }
     if (node == kDone) return h;
   }
-#else
-  for (;;) {
-    if (node < 0) {
-      const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)(~node) * kRunVec, ~node, ox, oy, dx, dy, inv_dd, skip_lo, skip_hi, h);
-      if (STATS) cnt.chords += looked;
-    } else {
-      if (STATS) cnt.nodes++;
-      const float4* np = reinterpret_cast<const float4*>(ac.nodes + node);
-      const float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1);
-      const float4 ch = load16<SMEM>(np + 2);
-      const int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
-      float le, re;
-      const float ln = slab_enter(sr, ox, oy, lb, &le);
-      const float rn = slab_enter(sr, ox, oy, rb, &re);
-      const float lim = h.t * RDC_CULL_SLACK;
-      const bool hl = ln <= le && ln <= lim;
-      const bool hr = rn <= re && rn <= lim;
-      if (hl && hr) {
-        const bool left_first = ln <= rn;
-        stack[sp++] = make_int2(left_first ? right : left, __float_as_int(left_first ? rn : ln));
-        node = left_first ? left : right;
-        continue;
-      }
-      if (hl || hr) {
-        node = hl ? left : right;
-        continue;
-      }
-    }
-    // pop the nearest pending subtree that still starts before the best hit
-    for (;;) {
-      if (sp == 0) return h;
-      const int2 e = stack[--sp];
-      if (__int_as_float(e.y) <= h.t * RDC_CULL_SLACK) {
-        node = e.x;
-        break;
-      }
-    }
-  }
-#endif
 }
 
 __device__ __forceinline__ void load_control_points(const DevScene& sc, uint32_t seg, rdc_f2 v[4]) {
