@@ -18,6 +18,7 @@
 //   * tree and table culling only use conservative tests (padded boxes, widened angular intervals, shrunk
 //     distances); the accepted hit is the lexicographic minimum of (t, chord id) over all chords, the same
 //     rule the brute-force oracle applies.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -80,6 +81,8 @@ struct RenderArgs {
   uint32_t local_rows;                  // rows of the output buffers this launch covers
   uint32_t row_skew;                    // row_begin % 4 of a contiguous band: tiles stay aligned to the full frame's
   uint32_t split;                       // work units per tile: unit q traces rays i = q (mod split)
+  uint32_t mid_tx, mid_ty;              // the tile (column, local tile row) nearest the scene's centre: units are handed out
+                                        // centre-out from it
   float4* part_rgbw;                    // [split][local pixels] partial sums of units (split > 1)
   float* part_blur;
   unsigned int* tile_arrivals;          // [tiles] units of the tile that have finished (self-rewinding)
@@ -514,6 +517,15 @@ __device__ __forceinline__ Sample trace_from(const RenderArgs& a, const Accel& a
   }
 }
 
+// k-th element of 0..n-1 ordered by distance from `mid`: mid, mid+1, mid-1, mid+2, ... and, once one side is used up, the rest
+// of the other. A bijection of [0,n) for every mid in [0,n).
+__device__ __forceinline__ uint32_t centre_out(uint32_t k, uint32_t mid, uint32_t n) {
+  const uint32_t lo = mid, hi = n - 1 - mid, m = lo < hi ? lo : hi;
+  if (k <= 2 * m) return (k & 1u) ? mid + (k + 1) / 2 : mid - k / 2;
+  const uint32_t rest = k - 2 * m;
+  return lo > hi ? mid - m - rest : mid + m + rest;
+}
+
 // Base direction of ray i: (1,0) rotated i times by the fp32 matrix of sincospi(2/N) — iterated, because
 // the accumulated rounding is part of the ray set (DeviceCode.cu:99,110-112,167-171). Pixel-independent,
 // so it is tabulated once per N.
@@ -822,7 +834,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   const uint32_t tiles_x = (a.width + kWarpTileW - 1) / kWarpTileW;
   // Tiles are cut on the full frame's grid (rows 0-3, 4-7, ...) whatever band this launch renders: a tile's run
   // table, and with it the order in which its pixels' rays are summed, must not depend on the band.
-  const uint32_t n_units = tiles_x * ((a.local_rows + a.row_skew + kWarpTileH - 1) / kWarpTileH) * a.split;
+  const uint32_t n_tile_rows = (a.local_rows + a.row_skew + kWarpTileH - 1) / kWarpTileH;
+  const uint32_t n_units = tiles_x * n_tile_rows * a.split;
   const uint32_t row_origin = a.row_begin - a.row_skew;
   const size_t part_stride = (size_t)a.local_rows * a.width;
   const bool small_angle = a.two_over_n <= 0.25f && a.two_over_n >= 0.0f;  // N >= 8: no range reduction (bit-identical)
@@ -834,7 +847,12 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     if (lane == 0) unit = atomicAdd(a.work, 1u);
     unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
     if (unit >= n_units) break;
-    const uint32_t tile = unit / a.split, q = unit % a.split;
+    // Units are handed out centre-out from the tile nearest the scene's centre, dearest first: a tile that looks at the scene
+    // from close by traces several times the rays of one far away, and a launch ends when its last unit does — with the long
+    // units up front the tail is made of short ones (a rank of 8 has 3.4 units per warp at 1080p: 0.264 ms where 0.221 is
+    // the mean). Which warp renders a tile when has no bearing on its pixels.
+    const uint32_t ord = unit / a.split, q = unit % a.split;
+    const uint32_t tile = centre_out(ord / tiles_x, a.mid_ty, n_tile_rows) * tiles_x + centre_out(ord % tiles_x, a.mid_tx, tiles_x);
     const uint32_t ix = (tile % tiles_x) * kWarpTileW + lane % kWarpTileW;
     const uint32_t vy = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local) + skew
     // row of the full image: contiguous band, or strip (vy / 16) of this rank's interleaved share
@@ -1472,6 +1490,22 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const int variant = L.variant;
   const size_t dyn = L.dyn;
   a.split = L.split;
+  {
+    // the scene's centre in pixels of the full frame (inverse of DeviceCode.cu:103-107), then in tiles of this launch
+    const float4 rb = s->dev.root_box;
+    const double z = p.zoom_factor != 0.0f ? (double)p.zoom_factor : 1.0;
+    const double px = (0.5 * ((double)rb.x + rb.z) - p.offset_x) / z + p.image_width / 2;
+    const double sy = (0.5 * ((double)rb.y + rb.w) - p.offset_y) / z;
+    const double py = p.use_diffusion_curve_save ? (double)p.image_height - (double)(p.image_height / 2) - sy : sy + p.image_height / 2;
+    const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
+    const uint32_t tile_rows = (L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH;
+    const double cx = std::fmin(std::fmax(px, 0.0), (double)p.image_width - 1.0);
+    const double cy = std::fmin(std::fmax(py, (double)p.row_begin), (double)p.row_end - 1.0) - (double)(p.row_begin - L.row_skew);
+    // strips: local row = (strip / stride) * 8 + row inside the strip, for the strips this launch renders
+    const double local_y = L.strip_stride > 1 ? std::floor(cy / kStripRows / L.strip_stride) * kStripRows + std::fmod(cy, (double)kStripRows) : cy;
+    a.mid_tx = std::min((uint32_t)(cx / kWarpTileW), tiles_x - 1);
+    a.mid_ty = std::min((uint32_t)(std::fmax(local_y, 0.0) / kWarpTileH), tile_rows - 1);
+  }
   a.part_rgbw = s->part_rgbw;
   a.part_blur = s->part_blur;
   a.tile_arrivals = s->tile_arrivals;
