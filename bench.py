@@ -426,14 +426,17 @@ class Workload:
     def kernel_roofline(self, reps):
         """k_render alone on this rank's share: work per ray from the counting build, time from CUDA events on its stream."""
         torch = self.torch
-        stats = torch.zeros((6,), dtype=torch.int64, device=self.dev)
+        stats = torch.zeros((9,), dtype=torch.int64, device=self.dev)
+        stats[6:8] = torch.iinfo(torch.int64).max  # the timeline slots take minima
         my_rows = sum(min(RDC_STRIP_ROWS, self.height - t * RDC_STRIP_ROWS)
                       for t in range(self.rank, (self.height + RDC_STRIP_ROWS - 1) // RDC_STRIP_ROWS, self.world)) if self.world > 1 else self.height
         p = self.my_share(0)
         p.stats = stats.data_ptr()
         self.scene.render(p, self.band.data_ptr(), self.sigma.data_ptr(), self.stream)
         torch.cuda.synchronize()
-        traced, nodes, chords, shaded, deferred, gathered = [float(x) for x in stats.cpu().tolist()]
+        host_stats = stats.cpu().tolist()
+        traced, nodes, chords, shaded, deferred, gathered = [float(x) for x in host_stats[:6]]
+        t_start, t_first_idle, t_last = host_stats[6:9]
         nodes += gathered
         rays = float(my_rows) * self.width * self.rpp
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -449,6 +452,7 @@ class Workload:
                "deferred_to_tree": deferred / rays, "table_query_nodes": gathered / rays}
         f_ray = F_GEN + per["nodes"] * F_NODE + per["chords"] * F_SEG + per["hits_shaded"] * F_SHADE + F_ACC
         b_ray = per["nodes"] * 32.0 + per["chords"] * 32.0  # L2-side bytes per ray
+        per["counting_build_timeline_ms"] = {"first_warp_out_of_work": (t_first_idle - t_start) * 1e-6, "last_warp_out": (t_last - t_start) * 1e-6}
         return {"rays": rays, "rows": my_rows, "kernel_ms": kernel_ms, "per_ray": per, "flops_per_ray": f_ray, "l2_bytes_per_ray": b_ray}
 
     def close(self):

@@ -140,12 +140,14 @@ typedef struct rdc_frame_params {
                                            ray's first hit, 0xFFFFFFFF for a miss (parity tests)       */
   float* max_sigma;                     /* optional device float: atomically raised to the largest
                                            blur_map value written (lets the blur skip all-zero maps)   */
-  unsigned long long* stats;            /* optional device uint64[6], atomically increased by: rays traced
+  unsigned long long* stats;            /* optional device uint64[9]; [0..5] atomically increased by: rays traced
                                            (continuations included), boxes tested (tree nodes and table
                                            slots), chords tested, hits shaded, primary rays the local run
-                                           table deferred to the tree, nodes visited by the table queries.
-                                           Selects a slower counting build of the kernel; feeds the
-                                           roofline's work-per-ray figure                */
+                                           table deferred to the tree, nodes visited by the table queries;
+                                           [6..8] the launch's timeline in ns of %globaltimer: start (set [6]
+                                           and [7] to ~0 beforehand: they take minima), first warp out of
+                                           work, last warp out. Selects a slower counting build of the
+                                           kernel; feeds the roofline's work-per-ray figure */
   int route;                            /* RDC_ROUTE_*; 0 = automatic                                    */
   uint32_t units_per_tile;              /* work units a tile's rays are dealt to: 0 = automatic (a function of
                                            the full frame only), else 1, 2 or 4. Part of the summation order:

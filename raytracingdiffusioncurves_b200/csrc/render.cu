@@ -842,6 +842,11 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   const float inf = __int_as_float(0x7f800000);
   float sigma_max = 0.0f;
   Counters cnt;
+  if (STATS && lane == 0) {  // launch timeline of the counting build: when did the launch start ...
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    atomicMin(a.stats + 6, now);
+  }
   for (;;) {
     uint32_t unit = 0;
     if (lane == 0) unit = atomicAdd(a.work, 1u);
@@ -1208,6 +1213,10 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       atomicAdd(a.stats + 3, (unsigned long long)h);
       atomicAdd(a.stats + 4, (unsigned long long)d);
       atomicAdd(a.stats + 5, (unsigned long long)g);
+      unsigned long long now;  // ... when did the first warp run out of work, when the last
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      atomicMin(a.stats + 7, now);
+      atomicMax(a.stats + 8, now);
     }
   }
   // the last warp to leave rewinds the tile counter for the next launch on this handle

@@ -61,7 +61,9 @@ class GpuRenderer:
         flag = torch.zeros((1,), dtype=torch.float32, device=dev)
         params.hit_ids = hits.data_ptr() if want_hits else None
         params.max_sigma = flag.data_ptr() if use_flag else None
-        stats = torch.zeros((6,), dtype=torch.int64, device=dev) if want_stats else None
+        stats = torch.zeros((9,), dtype=torch.int64, device=dev) if want_stats else None
+        if want_stats:
+            stats[6:8] = torch.iinfo(torch.int64).max  # launch timeline slots take minima
         params.stats = stats.data_ptr() if want_stats else None  # selects the counting build of the kernel
         stream = torch.cuda.current_stream().cuda_stream
         self.scene.render(params, image.data_ptr(), sigma.data_ptr(), stream)
@@ -79,7 +81,7 @@ class GpuRenderer:
             "blurred": blurred.cpu().numpy() if blur else None,
             "max_sigma": float(flag.item()),
             # rays traced, boxes tested, chords tested, hits shaded, rays deferred to the tree, nodes visited by table queries
-            "stats": stats.cpu().tolist() if want_stats else None,
+            "stats": stats.cpu().tolist()[:6] if want_stats else None,
         }
         return out
 
