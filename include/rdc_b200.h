@@ -149,9 +149,11 @@ typedef struct rdc_frame_params {
                                            work, last warp out. Selects a slower counting build of the
                                            kernel; feeds the roofline's work-per-ray figure */
   int route;                            /* RDC_ROUTE_*; 0 = automatic                                    */
-  uint32_t units_per_tile;              /* work units a tile's rays are dealt to: 0 = automatic (a function of
-                                           the full frame only), else 1, 2 or 4. Part of the summation order:
-                                           frames only compare bit for bit at equal values                */
+  uint32_t units_per_tile;              /* work units a tile's rays are dealt to: 0 = automatic (chosen per
+                                           launch from its size), else 1, 2, 4 or 8. Part of a pixel's
+                                           summation order: launches that must agree BIT FOR BIT (a frame
+                                           rendered whole and in bands, on 1 and on N GPUs) pin it to one
+                                           value; hit indices never depend on it and RGB moves by ~1e-7   */
   float local_radius;                   /* first radius (scene units) the local run table tries around a tile;
                                            0 = from the scene's density                                   */
 } rdc_frame_params;

@@ -398,6 +398,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   }
   rdc_scene* s = new rdc_scene();
   cudaGetDevice(&s->device);
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
   Uploader up{s, stream};
   DevScene& d = s->dev;
   bool portals = false;

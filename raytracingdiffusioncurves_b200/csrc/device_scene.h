@@ -83,6 +83,7 @@ struct DevScene {
 
 struct rdc_scene {
   int device = 0;
+  int sm_count = 0;  // multiprocessors of `device`
   DevScene dev{};
   rdc_scene_info info{};
   std::vector<void*> allocations;  // everything to cudaFree on destroy

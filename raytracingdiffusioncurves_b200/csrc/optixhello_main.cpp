@@ -36,6 +36,7 @@ static void usage_options() {
                "         --zoom Z --offset-x X --offset-y Y --seed S --max-depth D --tolerance T --curve-width R --endcap-size E\n"
                "         --weight-degree G --native (not an Orzan save) --no-blur --no-aa --denoiser (ignored) --brute-force\n"
                "         --device I --gpus N (the frame is split over N GPUs of this box, device I onwards)\n"
+               "         --units-per-tile U (1, 2, 4, 8; pins the summation order: the same pixels bit for bit on any number of GPUs)\n"
                "         --accumulate (running mean over frames, restarted when the view changes)\n"
                "         --scroll-at F:Y / --drag-at F:DX:DY (before frame F: the scroll / drag callbacks of glfw_events.cpp:105-130)\n";
 }
@@ -67,6 +68,7 @@ int main(int argc, char* argv[]) {
   float zoom = -1.0f, off_x = RDC_DEFAULT_OFFSET_X, off_y = RDC_DEFAULT_OFFSET_Y;
   unsigned seed = 0;
   int gpus = 1;
+  unsigned units_per_tile = 0;  // rdc_frame_params::units_per_tile: 0 = chosen per launch
   bool accumulate = false;
   struct ViewEvent {
     int frame;
@@ -105,6 +107,7 @@ int main(int argc, char* argv[]) {
     else if (a == "--brute-force") brute = true;
     else if (a == "--device") device = std::atoi(value());
     else if (a == "--gpus") gpus = std::atoi(value());
+    else if (a == "--units-per-tile") units_per_tile = (unsigned)std::atoi(value());
     else if (a == "--dump-f32") dump_path = value();
     else if (a == "--accumulate") accumulate = true;
     else if (a == "--scroll-at" || a == "--drag-at") {
@@ -166,6 +169,7 @@ int main(int argc, char* argv[]) {
   params.use_aa = use_aa;
   params.max_trace_depth = max_depth;
   params.traversal = brute ? RDC_TRAVERSAL_BRUTE_FORCE : RDC_TRAVERSAL_LBVH;
+  params.units_per_tile = units_per_tile;
   int halo_rows = 0;
   CALL_CHECK(rdc_host_scene_halo_rows(host, max_depth, &halo_rows));
 

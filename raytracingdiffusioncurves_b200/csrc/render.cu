@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a tile: 8x4 pixels, one lane per pixel, all lanes on the same ray index
-constexpr int kMaxSplit = 4;                    // a tile's rays may be dealt to up to 4 work units (RenderArgs::split)
+constexpr int kMaxSplit = 8;                    // a tile's rays may be dealt to up to 8 work units (RenderArgs::split)
+constexpr int kAutoSplit = 4;                   // ... of which the automatic choice uses up to 4
 constexpr uint32_t kTableRuns = 64;             // scenes with at most this many runs use the whole-scene run table
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");
@@ -1265,8 +1266,8 @@ int check_params(const rdc_frame_params& p) {
     set_error("render: unknown route %d", p.route);
     return RDC_E_INVALID;
   }
-  if (p.units_per_tile != 0 && p.units_per_tile != 1 && p.units_per_tile != 2 && p.units_per_tile != 4) {
-    set_error("render: units_per_tile must be 0 (automatic), 1, 2 or 4");
+  if (p.units_per_tile != 0 && p.units_per_tile != 1 && p.units_per_tile != 2 && p.units_per_tile != 4 && p.units_per_tile != (uint32_t)kMaxSplit) {
+    set_error("render: units_per_tile must be 0 (automatic), 1, 2, 4 or 8");
     return RDC_E_INVALID;
   }
   if (!(p.local_radius >= 0.0f)) {
@@ -1317,20 +1318,25 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
           (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0);
   // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table
   L.variant = (L.smem ? 1 : 0) | ((L.portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (L.table ? 8 : 0) | (L.local ? 16 : 0);
-  // Units per tile. It must not depend on how the frame is divided among GPUs (the summation order is part of
-  // the result), so it is a function of the full frame only: enough for about 200 k units in the frame (40 per
-  // warp of one GPU; every unit pays for its run table, and at 3840x2160 one unit per tile measured 8 % faster
-  // than four), at most kMaxSplit, while each unit keeps at least 16 rays and the partial sums fit 2 GiB.
+  // Units per tile: how many work units a tile's rays are dealt to (unit q traces rays i = q mod split; the units' partial
+  // sums are added in unit order). More units balance a launch better, fewer cost less: every unit pays for its run table
+  // and its partial sums, and the rays of a unit lie `split` strata apart, which makes the previous ray's hit a worse
+  // guess for the next (2.72 chords tested per ray at 4 units against 2.44 at 1 on the headline frame). Measured on the
+  // headline frame and on a rank's share of it at 2, 4 and 8 GPUs (profiles/r02c/timeline.log): the fastest choice is the
+  // one that leaves a warp about 13 units — 1 unit per tile for the whole 1080p frame (1.606 ms against 1.747 at 4), 2 for
+  // half of it, 4 for a quarter or less. So: the smallest count that gives this LAUNCH at least 12 units per resident warp.
+  // The count is part of a pixel's summation order: launches that must agree bit for bit (a frame rendered whole and in
+  // parts) pin rdc_frame_params::units_per_tile; hit indices never depend on it.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
-  const uint64_t frame_tiles = (uint64_t)tiles_x * ((p.image_height + kWarpTileH - 1) / kWarpTileH);
-  uint32_t split = 1;
-  while (split < (uint32_t)kMaxSplit && frame_tiles * split < 200000ull) split <<= 1;
-  if (p.units_per_tile) split = p.units_per_tile;
-  // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
-  while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * p.image_width * p.image_height * 20ull > (2ull << 30))) split >>= 1;
-  L.split = split;
   L.local_pixels = (size_t)L.local_rows * p.image_width;
   L.local_tiles = tiles_x * ((L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH);
+  const uint64_t warps = (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) * RDC_MIN_BLOCKS * (kBlock / 32);
+  uint32_t split = 1;
+  while (split < (uint32_t)kAutoSplit && (uint64_t)L.local_tiles * split < 12ull * warps) split <<= 1;
+  if (p.units_per_tile) split = p.units_per_tile;
+  // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
+  while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * L.local_pixels * 20ull > (2ull << 30))) split >>= 1;
+  L.split = split;
   return L;
 }
 
@@ -1413,9 +1419,21 @@ int reserve(rdc_scene* s, const rdc_frame_params& p, cudaStream_t stream) {
     return RDC_E_INVALID;
   }
   if (int rc = check_params(p)) return rc;
-  // the widest plan the parameters can lead to: the counting build and both routes share the same scratch sizes
-  const LaunchPlan L = plan_launch(s, p);
+  // the frame itself and every share of it a rank of 2..RDC_MAX_FRAME_TARGETS GPUs may be asked for (rdc_peer_*): a smaller
+  // launch may deal its tiles to more units and so need partial sums the whole frame does not
+  LaunchPlan L = plan_launch(s, p);
   if (L.local_rows == 0) return 0;
+  for (uint32_t stride = 2; stride <= RDC_MAX_FRAME_TARGETS; ++stride) {
+    rdc_frame_params q = p;
+    q.strip_stride = stride;
+    q.strip_offset = 0;
+    const LaunchPlan S = plan_launch(s, q);
+    if (S.split > 1 && S.local_pixels * S.split > (L.split > 1 ? L.local_pixels * L.split : 0)) {
+      L.local_pixels = S.local_pixels;
+      L.split = S.split;
+    }
+    if (S.local_tiles > L.local_tiles) L.local_tiles = S.local_tiles;
+  }
   RenderKernel kernel = nullptr;
   if (int rc = prepare_variant(s, L, &kernel)) return rc;
   cudaFuncAttributes fa;

@@ -11,8 +11,8 @@ RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-add
 timeout 600 $RUN tools/check_bands_gpu.py > $OUT/bands_check.log 2>&1; echo "bands check exit: $?" >> $OUT/bands_check.log
 timeout 300 python -m pytest tests/test_peer_frames_gpu.py -m gpu -q -x > $OUT/pytest_peer.log 2>&1; echo "pytest exit: $?" >> $OUT/pytest_peer.log
 for g in 1 $N; do
-  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/arch.xml 128 --width 1920 --height 1080 --frames 50 --gpus $g --dump-f32 $OUT/arch_$g.f32 > $OUT/optixhello_arch_$g.log 2>&1
-  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/DiffusionCurvePack/lady_bug.xml 128 --width 1920 --height 1080 --frames 20 --gpus $g --dump-f32 $OUT/lady_$g.f32 > $OUT/optixhello_lady_$g.log 2>&1
+  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/arch.xml 128 --width 1920 --height 1080 --frames 50 --gpus $g --units-per-tile 4 --dump-f32 $OUT/arch_$g.f32 > $OUT/optixhello_arch_$g.log 2>&1
+  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/DiffusionCurvePack/lady_bug.xml 128 --width 1920 --height 1080 --frames 20 --gpus $g --units-per-tile 1 --dump-f32 $OUT/lady_$g.f32 > $OUT/optixhello_lady_$g.log 2>&1
 done
 cmp $OUT/arch_1.f32 $OUT/arch_$N.f32 && echo "OptixHello arch: 1 GPU == $N GPUs" > $OUT/optixhello_cmp.log
 cmp $OUT/lady_1.f32 $OUT/lady_$N.f32 && echo "OptixHello lady_bug: 1 GPU == $N GPUs" >> $OUT/optixhello_cmp.log

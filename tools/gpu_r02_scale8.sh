@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=index,name,clocks.sm --format=csv > $OUT/smi.txt 2>&1
 run() { local n=$1; shift; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 "$@"; }
 run 8 tools/check_bands_gpu.py > $OUT/bands_check_8.log 2>&1; echo "bands check exit: $?" >> $OUT/bands_check_8.log
 for g in 1 8; do
-  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/arch.xml 128 --width 1920 --height 1080 --frames 50 --gpus $g --dump-f32 $OUT/arch_$g.f32 > $OUT/optixhello_arch_$g.log 2>&1
+  timeout 120 raytracingdiffusioncurves_b200/OptixHello tests/golden/xmls/arch.xml 128 --width 1920 --height 1080 --frames 50 --gpus $g --units-per-tile 4 --dump-f32 $OUT/arch_$g.f32 > $OUT/optixhello_arch_$g.log 2>&1
 done
 cmp $OUT/arch_1.f32 $OUT/arch_8.f32 && echo "OptixHello arch: 1 GPU == 8 GPUs" > $OUT/optixhello_cmp.log
 rm -f $OUT/*.f32
