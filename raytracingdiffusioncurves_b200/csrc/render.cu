@@ -32,7 +32,7 @@ namespace {
 constexpr int kBlock = 256;
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // a tile: 8x4 pixels, one lane per pixel, all lanes on the same ray index
 constexpr int kMaxSplit = 8;                    // a tile's rays may be dealt to up to 8 work units (RenderArgs::split)
-constexpr int kAutoSplit = 4;                   // ... of which the automatic choice uses up to 4
+constexpr int kAutoSplit = 8;                   // (the automatic choice may use all of them: a rank of 8 at 1080p does)
 constexpr uint32_t kTableRuns = 64;             // scenes with at most this many runs use the whole-scene run table
 constexpr int kStripRows = RDC_STRIP_ROWS;       // multi-GPU strips (rdc_frame_params::strip_stride)
 static_assert(kStripRows % kWarpTileH == 0, "a warp tile must not straddle two strips");

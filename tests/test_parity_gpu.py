@@ -110,6 +110,33 @@ def test_portals_iterative_retrace(depth, xml_dir, api, port_oracle):
     compare_images(out["image"], oimg, RGB_TOL)
 
 
+@pytest.mark.parametrize("name", ["arch.xml", "DiffusionCurvePack/lady_bug.xml"])
+def test_units_per_tile_only_moves_the_summation_order(name, xml_dir, api, port_oracle):
+    """1, 2, 4 or 8 work units per tile (the library picks one per launch): the same first hits bit for bit, pixels within
+    the rounding of a differently ordered sum, each within the parity tolerance of the oracle; pinned, a frame rendered in
+    bands equals the one-call frame bit for bit."""
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    w, h, n = 64, 48, 128
+    zoom = scene["image_height"] / h
+    oimg, _, ohits = port_oracle.render(scene, po.make_params(w, h, n, zoom_factor=zoom), want_hits=True, search="grid")
+    r = GpuRenderer(path)
+    images = []
+    for units in (1, 2, 4, 8):
+        out = r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, units_per_tile=units), want_hits=True)
+        assert np.array_equal(out["hits"], ohits), units
+        compare_images(out["image"], oimg, RGB_TOL)
+        images.append(out["image"])
+        parts = [r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, units_per_tile=units, row_begin=b, row_end=e))["image"]
+                 for b, e in ((0, 20), (20, 48))]
+        assert np.array_equal(bits(np.concatenate(parts)), bits(out["image"])), units
+    for img in images[1:]:
+        m = ~np.isnan(images[0])
+        assert np.max(np.abs(img[m] - images[0][m])) <= 2e-6
+    with pytest.raises(api.RdcError):
+        r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, units_per_tile=3))
+
+
 def test_row_bands_concatenate_bit_exactly(xml_dir, api):
     """Partition invariance: 1-GPU image == concatenation of bands, bit for bit."""
     r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))
