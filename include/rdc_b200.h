@@ -79,6 +79,9 @@ void rdc_free(void* p);
  *      OPTIX_PRIMITIVE_TYPE_ROUND_CUBIC_BSPLINE (optixHello.cpp:765-830) and the per-array
  *      cudaMallocAsync+cudaMemcpyAsync uploads (:524-762) ---- */
 
+#define RDC_TREE_AUTO 0   /* surface-area heuristic up to 65 536 runs, Morton radix tree above                 */
+#define RDC_TREE_MORTON 1 /* Morton-code radix tree (Karras 2012), built on the GPU                           */
+#define RDC_TREE_SAH 2    /* binned surface-area heuristic, built on the host                                 */
 typedef struct rdc_accel_options {
   float curve_width;         /* optixHello.cpp:95 (1e-3): pads chord boxes                          */
   float flatness_tolerance;  /* max |curve - chord| in XML pixels; chords per segment follow from it */
@@ -86,6 +89,7 @@ typedef struct rdc_accel_options {
   int run_length;            /* chords per tree leaf, 1..8; 0 = choose from the scene's density        */
   int shading_records;       /* per-chord 128-byte shading records: 0 = library default (built when the
                                 table fits 32 MB), -1 = never (shading walks the stop lists)            */
+  int tree;                  /* RDC_TREE_*: how the tree over the leaf runs is built; same results either way */
 } rdc_accel_options;
 
 typedef struct rdc_scene rdc_scene; /* opaque: device-resident SoA scene + chords + LBVH, one per device */

@@ -295,7 +295,7 @@ class SceneArrays(C.Structure):
 
 class AccelOptions(C.Structure):
     _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int),
-                ("run_length", C.c_int), ("shading_records", C.c_int)]
+                ("run_length", C.c_int), ("shading_records", C.c_int), ("tree", C.c_int)]
 
 
 class FrameParams(C.Structure):
@@ -353,7 +353,7 @@ def make_params(width, height, rays_per_pixel, **kw) -> FrameParams:
 
 
 def make_accel(curve_width=1e-3, flatness_tolerance=0.05, max_chords_per_segment=1024) -> AccelOptions:
-    return AccelOptions(curve_width, flatness_tolerance, max_chords_per_segment, 0, 0)
+    return AccelOptions(curve_width, flatness_tolerance, max_chords_per_segment, 0, 0, 0)
 
 
 def build(verbose: bool = False) -> None:

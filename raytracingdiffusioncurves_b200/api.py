@@ -50,7 +50,7 @@ class SceneArrays(C.Structure):
 
 class AccelOptions(C.Structure):
     _fields_ = [("curve_width", C.c_float), ("flatness_tolerance", C.c_float), ("max_chords_per_segment", C.c_int),
-                ("run_length", C.c_int), ("shading_records", C.c_int)]
+                ("run_length", C.c_int), ("shading_records", C.c_int), ("tree", C.c_int)]
 
 
 class SceneInfo(C.Structure):
@@ -76,6 +76,7 @@ class FrameParams(C.Structure):
 TRAVERSAL_LBVH = 0
 TRAVERSAL_BRUTE_FORCE = 1
 ROUTE_AUTO, ROUTE_TREE, ROUTE_LOCAL_TABLE = 0, 1, 2
+TREE_AUTO, TREE_MORTON, TREE_SAH = 0, 1, 2
 
 # every symbol include/rdc_b200.h declares, with its prototype (tests check the library exports them all)
 PROTOTYPES = {

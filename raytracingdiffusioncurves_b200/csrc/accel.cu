@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <algorithm>
 #include <vector>
 
 #include "device_scene.h"
@@ -345,13 +346,140 @@ void destroy_scene(rdc_scene* s) {
   delete s;
 }
 
+// ---- binned surface-area-heuristic tree over the runs' boxes, built on the host -------------------------------------
+// The Morton radix tree (k_radix_tree) splits where the codes' bits say; this one splits where the expected number of box
+// tests says: in 2-D a random line meets a convex shape with probability proportional to its perimeter, so a split costs
+// perimeter(left) * count(left) + perimeter(right) * count(right). Top-down, 16 bins per axis, both axes tried. Same leaves
+// (runs in Morton order), same node layout, so traversal, table queries and every result are untouched — only the number
+// of nodes and leaves a ray has to look at changes. Scenes up to kSahMaxRuns runs (the build is O(n log n) on one core).
+constexpr uint32_t kSahMaxRuns = 1u << 16;
+
+namespace {
+struct HostBox {
+  float x0, y0, x1, y1;
+  void grow(const HostBox& b) {
+    x0 = std::fmin(x0, b.x0); y0 = std::fmin(y0, b.y0); x1 = std::fmax(x1, b.x1); y1 = std::fmax(y1, b.y1);
+  }
+  float perimeter() const { return (x1 - x0) + (y1 - y0); }
+};
+
+inline HostBox empty_box() {
+  const float inf = std::numeric_limits<float>::infinity();
+  return HostBox{inf, inf, -inf, -inf};
+}
+
+// Returns the depth of the tree (leaves at depth >= 1), or 0 when it grew deeper than `max_depth`.
+unsigned sah_build(const std::vector<float4>& leaf, float pad, std::vector<BvhNode>& nodes, unsigned max_depth) {
+  const int n = (int)leaf.size();
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  nodes.assign((size_t)n - 1, BvhNode{});
+  struct Task {
+    int lo, hi, node, parent;
+    unsigned depth;
+  };
+  auto bounds_of = [&](int lo, int hi) {
+    HostBox b = empty_box();
+    for (int i = lo; i < hi; ++i) b.grow(HostBox{leaf[order[i]].x, leaf[order[i]].y, leaf[order[i]].z, leaf[order[i]].w});
+    return b;
+  };
+  auto padded_box = [&](const HostBox& b) { return make_float4(b.x0 - pad, b.y0 - pad, b.x1 + pad, b.y1 + pad); };
+  int next_node = 1;
+  unsigned depth = 1;
+  std::vector<Task> stack{Task{0, n, 0, -1, 1}};
+  constexpr int kBins = 16;
+  while (!stack.empty()) {
+    const Task t = stack.back();
+    stack.pop_back();
+    if (t.depth + 1 > max_depth) return 0;
+    depth = std::max(depth, t.depth + 1);
+    const int count = t.hi - t.lo;
+    // centroid bounds of the range
+    float cx0 = INFINITY, cy0 = INFINITY, cx1 = -INFINITY, cy1 = -INFINITY;
+    for (int i = t.lo; i < t.hi; ++i) {
+      const float4 b = leaf[order[i]];
+      const float cx = 0.5f * (b.x + b.z), cy = 0.5f * (b.y + b.w);
+      cx0 = std::fmin(cx0, cx); cx1 = std::fmax(cx1, cx); cy0 = std::fmin(cy0, cy); cy1 = std::fmax(cy1, cy);
+    }
+    int best_axis = -1, best_bin = -1;
+    float best_cost = INFINITY;
+    for (int axis = 0; axis < 2 && count > 2; ++axis) {
+      const float lo = axis ? cy0 : cx0, hi = axis ? cy1 : cx1;
+      if (!(hi > lo)) continue;
+      const float scale = kBins / (hi - lo);
+      HostBox bin_box[kBins];
+      int bin_count[kBins] = {};
+      for (int b = 0; b < kBins; ++b) bin_box[b] = empty_box();
+      for (int i = t.lo; i < t.hi; ++i) {
+        const float4 b = leaf[order[i]];
+        const float c = axis ? 0.5f * (b.y + b.w) : 0.5f * (b.x + b.z);
+        const int k = std::min(kBins - 1, std::max(0, (int)((c - lo) * scale)));
+        bin_box[k].grow(HostBox{b.x, b.y, b.z, b.w});
+        bin_count[k]++;
+      }
+      float right_cost[kBins];
+      HostBox acc = empty_box();
+      int cnt = 0;
+      for (int k = kBins - 1; k > 0; --k) {
+        if (bin_count[k]) acc.grow(bin_box[k]);
+        cnt += bin_count[k];
+        right_cost[k] = cnt ? acc.perimeter() * (float)cnt : INFINITY;
+      }
+      acc = empty_box();
+      cnt = 0;
+      for (int k = 0; k < kBins - 1; ++k) {
+        if (bin_count[k]) acc.grow(bin_box[k]);
+        cnt += bin_count[k];
+        if (cnt == 0 || cnt == count) continue;
+        const float cost = acc.perimeter() * (float)cnt + right_cost[k + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = axis;
+          best_bin = k;
+        }
+      }
+    }
+    int mid;
+    if (best_axis < 0) {
+      mid = t.lo + count / 2;  // two leaves, or all centroids in one place: split the (Morton-ordered) range in the middle
+    } else {
+      const float lo = best_axis ? cy0 : cx0, hi = best_axis ? cy1 : cx1;
+      const float scale = kBins / (hi - lo);
+      auto in_left = [&](int r) {
+        const float4 b = leaf[r];
+        const float c = best_axis ? 0.5f * (b.y + b.w) : 0.5f * (b.x + b.z);
+        return std::min(kBins - 1, std::max(0, (int)((c - lo) * scale))) <= best_bin;
+      };
+      mid = (int)(std::stable_partition(order.begin() + t.lo, order.begin() + t.hi, in_left) - order.begin());
+      if (mid == t.lo || mid == t.hi) mid = t.lo + count / 2;
+    }
+    BvhNode& node = nodes[t.node];
+    node.parent = t.parent;
+    node.pad = 0;
+    node.lbox = padded_box(bounds_of(t.lo, mid));
+    node.rbox = padded_box(bounds_of(mid, t.hi));
+    if (mid - t.lo == 1) node.left = ~order[t.lo];
+    else {
+      node.left = next_node++;
+      stack.push_back(Task{t.lo, mid, node.left, t.node, t.depth + 1});
+    }
+    if (t.hi - mid == 1) node.right = ~order[mid];
+    else {
+      node.right = next_node++;
+      stack.push_back(Task{mid, t.hi, node.right, t.node, t.depth + 1});
+    }
+  }
+  return depth;
+}
+}  // namespace
+
 int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStream_t stream, rdc_scene** out) {
   if (a.n_segments == 0 || a.n_curves == 0 || a.n_vertices < 4) {
     set_error("accel: empty scene");
     return RDC_E_INVALID;
   }
   if (!(o.flatness_tolerance > 0.0f) || o.max_chords_per_segment < 1 || !(o.curve_width >= 0.0f) || o.run_length < 0 ||
-      o.run_length > RDC_RUN) {
+      o.run_length > RDC_RUN || o.tree < RDC_TREE_AUTO || o.tree > RDC_TREE_SAH) {
     set_error("accel: bad options");
     return RDC_E_INVALID;
   }
@@ -671,17 +799,34 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   k_pad_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, n_runs, pad, run_box, extent_sums);
   TEMP_CUDA(cudaGetLastError());
   TEMP_CUDA(cudaMemsetAsync(max_depth, 0, sizeof(unsigned int), stream));
+  unsigned int sah_depth = 0;
   if (n_runs == 1) {
     k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_box, pad, nodes);
     TEMP_CUDA(cudaGetLastError());
   } else {
-    TEMP_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
-    k_radix_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>(codes, (int)n_runs, nodes, leaf_parent);
-    TEMP_CUDA(cudaGetLastError());
-    k_fit_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, (int)n_runs, pad, leaf_parent, nodes, node_box, arrivals);
-    TEMP_CUDA(cudaGetLastError());
-    k_depth<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_runs, max_depth);
-    TEMP_CUDA(cudaGetLastError());
+    // tree over the runs: surface-area heuristic on the host for scenes it handles in milliseconds, Morton radix tree on
+    // the device otherwise (or when the SAH tree comes out deeper than the traversal stack)
+    const bool want_sah = o.tree == RDC_TREE_SAH || (o.tree == RDC_TREE_AUTO && n_runs <= kSahMaxRuns);
+    if (want_sah) {
+      std::vector<float4> h_leaf(n_runs);
+      TEMP_CUDA(cudaMemcpyAsync(h_leaf.data(), leaf_box, n_runs * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+      TEMP_CUDA(cudaStreamSynchronize(stream));
+      std::vector<BvhNode> h_nodes;
+      sah_depth = sah_build(h_leaf, pad, h_nodes, 62);
+      if (sah_depth) {
+        TEMP_CUDA(cudaMemcpyAsync(nodes, h_nodes.data(), h_nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, stream));
+        TEMP_CUDA(cudaStreamSynchronize(stream));  // h_nodes leaves scope
+      }
+    }
+    if (!sah_depth) {
+      TEMP_CUDA(cudaMemsetAsync(arrivals, 0, n_nodes * sizeof(unsigned int), stream));
+      k_radix_tree<<<blocks_for(n_runs - 1), kThreads, 0, stream>>>(codes, (int)n_runs, nodes, leaf_parent);
+      TEMP_CUDA(cudaGetLastError());
+      k_fit_boxes<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_box, (int)n_runs, pad, leaf_parent, nodes, node_box, arrivals);
+      TEMP_CUDA(cudaGetLastError());
+      k_depth<<<blocks_for(n_runs), kThreads, 0, stream>>>(leaf_parent, nodes, (int)n_runs, max_depth);
+      TEMP_CUDA(cudaGetLastError());
+    }
   }
   unsigned int depth = 0;
   unsigned long long h_extent[2] = {0, 0};
@@ -689,6 +834,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
   TEMP_CUDA(cudaMemcpyAsync(&depth, max_depth, sizeof depth, cudaMemcpyDeviceToHost, stream));
   TEMP_CUDA(cudaStreamSynchronize(stream));
   free_temps();
+  if (sah_depth) depth = sah_depth;
   if (depth > 62) {
     set_error("accel: tree depth %u exceeds the traversal stack", depth);
     return fail(RDC_E_LIMIT);

@@ -255,6 +255,7 @@ void rdc_default_accel_options(rdc_accel_options* o) {
   o->max_chords_per_segment = 1024;
   o->run_length = 0;
   o->shading_records = 0;
+  o->tree = RDC_TREE_AUTO;
 }
 
 int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out) {

@@ -137,6 +137,32 @@ def test_units_per_tile_only_moves_the_summation_order(name, xml_dir, api, port_
         r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, units_per_tile=3))
 
 
+@pytest.mark.parametrize("name", ["DiffusionCurvePack/lady_bug.xml", "DiffusionCurvePack/dolphin.xml", "PortalDemo.xml", "test2.xml"])
+def test_tree_builders_give_the_same_frame(name, xml_dir, api, port_oracle):
+    """Morton radix tree (GPU) and binned surface-area-heuristic tree (host): different trees over the same leaves — the same
+    first hits and the same pixels bit for bit, on the tree route and on the automatic one, and both equal to the oracle."""
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    w, h, n = 72, 52, 16
+    zoom = scene["image_height"] / h
+    oimg, _, ohits = port_oracle.render(scene, po.make_params(w, h, n, zoom_factor=zoom), want_hits=True, search="grid")
+    outs, boxes = {}, {}
+    for tree in (api.TREE_MORTON, api.TREE_SAH):
+        r = GpuRenderer(path, accel=api.default_accel_options(tree=tree))
+        assert r.scene.stats.n_nodes == max(r.scene.stats.n_runs - 1, 1) and 1 <= r.scene.stats.bvh_depth <= 62
+        for route in (api.ROUTE_TREE, api.ROUTE_AUTO):
+            out = r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, route=route), want_hits=True, want_stats=True)
+            assert np.array_equal(out["hits"], ohits), (tree, route)
+            compare_images(out["image"], oimg, RGB_TOL)
+            outs[(tree, route)] = out["image"]
+            boxes[(tree, route)] = out["stats"][1]
+    for route in (api.ROUTE_TREE, api.ROUTE_AUTO):
+        assert np.array_equal(bits(outs[(api.TREE_MORTON, route)]), bits(outs[(api.TREE_SAH, route)])), route
+    print(f"{name}: boxes tested on the tree route: Morton {boxes[(api.TREE_MORTON, api.ROUTE_TREE)]}, SAH {boxes[(api.TREE_SAH, api.ROUTE_TREE)]}")
+    with pytest.raises(api.RdcError):
+        GpuRenderer(path, accel=api.default_accel_options(tree=7))
+
+
 def test_row_bands_concatenate_bit_exactly(xml_dir, api):
     """Partition invariance: 1-GPU image == concatenation of bands, bit for bit."""
     r = GpuRenderer(os.path.join(xml_dir, "DiffusionCurvePack/zephyr.xml"))

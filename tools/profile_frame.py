@@ -23,7 +23,7 @@ def main():
     host = api.HostScene.from_xml_file(payload) if kind == "file" else api.HostScene.from_xml_text(payload)
     stream = torch.cuda.current_stream().cuda_stream
     run_length = int(os.environ.get("RDC_RUN_LENGTH", "0"))
-    scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length), stream)
+    scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length, tree=int(os.environ.get("RDC_TREE", "0"))), stream)
     # RDC_PROFILE_ROWS=a:b: only that band of the frame (full-size frames of the largest workloads take seconds)
     row_begin, row_end = 0, height
     if os.environ.get("RDC_PROFILE_ROWS"):

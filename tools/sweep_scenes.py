@@ -49,7 +49,8 @@ def main():
         name = os.path.relpath(path, XML_DIR)
         host = api.HostScene.from_xml_file(path)
         run_length = int(os.environ.get("RDC_RUN_LENGTH", "0"))  # tuning: chords per leaf (0 = the library's choice)
-        scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length), torch.cuda.current_stream().cuda_stream)
+        tree = int(os.environ.get("RDC_TREE", "0"))  # api.TREE_*: 0 automatic, 1 Morton radix tree, 2 surface-area heuristic
+        scene = api.Scene(host.arrays, api.default_accel_options(run_length=run_length, tree=tree), torch.cuda.current_stream().cuda_stream)
         zoom = host.arrays.image_height / height
         render_ms, blur_ms, smax = time_frames(scene, width, height, rpp, zoom)
         row = {"scene": name, "runs": scene.stats.n_runs, "chords": scene.stats.n_chords, "render_ms": round(render_ms, 3),
