@@ -120,9 +120,11 @@ void rdc_scene_destroy(rdc_scene* scene);
 #define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
 /* how primary rays find their closest chord (rdc_frame_params::route); every route gives the same bits */
 #define RDC_ROUTE_AUTO 0        /* whole-scene run table up to 64 runs, per-tile local run table for large scenes
-                                   seen closely enough, the tree otherwise                                    */
+                                   seen closely enough, the cut table for the scenes in between               */
 #define RDC_ROUTE_TREE 1        /* always the LBVH                                                            */
 #define RDC_ROUTE_LOCAL_TABLE 2 /* per-tile local run table whatever the size of the scene                     */
+#define RDC_ROUTE_CUT_TABLE 3   /* per-tile table over a 64-entry cut through the tree (scenes of more than 64 runs
+                                   that have a surface-area tree)                                              */
 
 typedef struct rdc_frame_params {
   uint32_t image_width, image_height;   /* output size (params.h:48-49)                               */

@@ -75,7 +75,7 @@ class FrameParams(C.Structure):
 
 TRAVERSAL_LBVH = 0
 TRAVERSAL_BRUTE_FORCE = 1
-ROUTE_AUTO, ROUTE_TREE, ROUTE_LOCAL_TABLE = 0, 1, 2
+ROUTE_AUTO, ROUTE_TREE, ROUTE_LOCAL_TABLE, ROUTE_CUT_TABLE = 0, 1, 2, 3
 TREE_AUTO, TREE_MORTON, TREE_SAH = 0, 1, 2
 
 # every symbol include/rdc_b200.h declares, with its prototype (tests check the library exports them all)

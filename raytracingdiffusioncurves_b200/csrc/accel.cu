@@ -471,6 +471,39 @@ unsigned sah_build(const std::vector<float4>& leaf, float pad, std::vector<BvhNo
   }
   return depth;
 }
+
+// A cut through the tree for the per-tile table of mid-size scenes: start from the root's two children and keep opening
+// the entry that costs most — perimeter of its box times the runs below it — until there are `max_entries` of them or only
+// leaves are left. Entries: node index (subtree) or ~run (leaf); boxes are the padded child boxes the nodes carry.
+void tree_cut(const std::vector<BvhNode>& nodes, int n_runs, int max_entries, std::vector<int>& entry, std::vector<float4>& box) {
+  // runs below every inner node (children are created after their parents: a reverse sweep sees children first)
+  std::vector<int> below(nodes.size(), 0);
+  for (int i = (int)nodes.size() - 1; i >= 0; --i) {
+    const BvhNode& nd = nodes[i];
+    below[i] = (nd.left < 0 ? 1 : below[nd.left]) + (nd.right < 0 ? 1 : below[nd.right]);
+  }
+  (void)n_runs;
+  entry = {nodes[0].left, nodes[0].right};
+  box = {nodes[0].lbox, nodes[0].rbox};
+  while ((int)entry.size() < max_entries) {
+    int pick = -1;
+    float worst = -1.0f;
+    for (size_t e = 0; e < entry.size(); ++e) {
+      if (entry[e] < 0) continue;
+      const float cost = ((box[e].z - box[e].x) + (box[e].w - box[e].y)) * (float)below[entry[e]];
+      if (cost > worst) {
+        worst = cost;
+        pick = (int)e;
+      }
+    }
+    if (pick < 0) break;
+    const BvhNode& nd = nodes[entry[pick]];
+    entry[pick] = nd.left;
+    box[pick] = nd.lbox;
+    entry.push_back(nd.right);
+    box.push_back(nd.rbox);
+  }
+}
 }  // namespace
 
 int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStream_t stream, rdc_scene** out) {
@@ -815,7 +848,17 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
       sah_depth = sah_build(h_leaf, pad, h_nodes, 62);
       if (sah_depth) {
         TEMP_CUDA(cudaMemcpyAsync(nodes, h_nodes.data(), h_nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, stream));
-        TEMP_CUDA(cudaStreamSynchronize(stream));  // h_nodes leaves scope
+        std::vector<int> cut_entry;
+        std::vector<float4> cut_boxes;
+        tree_cut(h_nodes, (int)n_runs, 64, cut_entry, cut_boxes);
+        d.cut_node = up.upload(cut_entry.data(), cut_entry.size());
+        d.cut_box = up.upload(cut_boxes.data(), cut_boxes.size());
+        d.n_cut = (uint32_t)cut_entry.size();
+        TEMP_CUDA(cudaStreamSynchronize(stream));  // h_nodes and the cut leave scope
+        if (up.status) {
+          free_temps();
+          return fail(up.status);
+        }
       }
     }
     if (!sah_depth) {

@@ -77,6 +77,11 @@ struct DevScene {
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K
   const float4* run_box;           // [n_runs] Morton order: padded box of each run (per-tile run table)
   const BvhNode* nodes;            // [max(n_runs-1,1)]
+  // cut through the tree: at most 64 subtrees (node index) or leaves (~run) that together hold every run, with their padded
+  // boxes — the slots of the per-tile table of mid-size scenes (render.cu, kModeCut). n_cut == 0: no cut (Morton trees).
+  const int* cut_node;
+  const float4* cut_box;
+  uint32_t n_cut;
   float4 root_box;                 // padded box of the whole scene (per-pixel angular culling)
   uint32_t n_segments, n_curves, n_chords, n_runs, n_nodes;
 };
@@ -97,7 +102,7 @@ struct rdc_scene {
   cudaEvent_t launched = nullptr;
   cudaStream_t launched_on = nullptr;
   bool launched_any = false;
-  uint32_t grid_blocks[32] = {};  // SM-filling grid size per kernel variant
+  uint32_t grid_blocks[64] = {};  // SM-filling grid size per kernel variant
   float mean_run_w = 0.0f, mean_run_h = 0.0f;  // mean padded run box (local-table radius estimate)
   // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
   float4* part_rgbw = nullptr;

@@ -53,7 +53,7 @@ constexpr int kGatherAttempts = 6;                // radius adjustments per work
 constexpr int kDeferCap = 64;                     // deferred rays a warp can hold (a batch of 32 leaves when 32 are waiting)
 constexpr int kRingWords = kGatherCap > 2 * kDeferCap ? kGatherCap : 2 * kDeferCap;
 static_assert(kGatherCap <= 256, "candidate keys carry the position in their low 8 bits");
-enum { kModeTree = 0, kModeTable = 1, kModeLocal = 2 };
+enum { kModeTree = 0, kModeTable = 1, kModeLocal = 2, kModeCut = 3 };
 
 struct __align__(16) WarpLocal {
   float4 box[kLocalSlots];        // padded box of the run in each slot; slots are sorted by distance from the tile
@@ -123,6 +123,10 @@ struct Accel {
   const float4* runs;     // kRunVec float4 per run
   const float4* run_box;  // padded box per run
   uint32_t n_runs;
+  // per-tile table (kModeTable, kModeCut): padded box per table entry and, in cut mode, what the entry is — a subtree
+  // (node index) or a leaf (~run); kModeTable: entry = run, slot_node stays null
+  const float4* slot_box;
+  const int* slot_node;
 };
 
 // per-thread work counters of the counting build (rdc_frame_params::stats)
@@ -234,7 +238,32 @@ struct Slots {
   const float4* box;  // nullptr: the whole-scene table reads ac.run_box[run]
 };
 
-template <bool SMEM, bool PORTALS, bool STATS, bool LOCAL, int W>
+template <bool SMEM, bool PORTALS, bool STATS>
+__device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy, bool primary,
+                                             uint32_t skip_lo, uint32_t skip_hi, float bound, Counters& cnt, int root = 0,
+                                             bool whole_ray = true);
+
+// One table entry against the ray: a run (test_run), or — cut mode — everything below a node of the tree, walked with the
+// best hit so far as the bound. Returns true when the entry produced the new best hit.
+template <bool SMEM, bool PORTALS, bool STATS, bool CUT>
+__device__ __forceinline__ bool test_entry(const Accel& ac, int entry, float ox, float oy, float dx, float dy, Hit& h, Counters& cnt) {
+  const int ref = CUT ? ac.slot_node[entry] : ~entry;
+  if (!CUT || ref < 0) {
+    const int run = ~ref;
+    const uint32_t before = h.id;
+    const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
+    if (STATS) cnt.chords += looked;
+    return h.id != before;
+  }
+  const Hit sub = closest_chord<SMEM, PORTALS, STATS>(ac, false, ox, oy, dx, dy, true, 1u, 0u, h.t, cnt, ref, false);
+  if (sub.leaf >= 0 && rdc_hit_closer(sub.t, sub.id, h.t, h.id)) {
+    h = sub;
+    return true;
+  }
+  return false;
+}
+
+template <bool SMEM, bool PORTALS, bool STATS, bool LOCAL, bool CUT, int W>
 __device__ __forceinline__ Hit table_closest(const Accel& ac, const Slots& sl, uint32_t (&m)[W], int& last_slot, float ox,
                                              float oy, float dx, float dy, Counters& cnt) {
   Hit h;
@@ -256,12 +285,7 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const Slots& sl, u
         m[k] &= ~bit;
         there = true;
       }
-    if (there) {
-      const int run = (int)sl.run[last_slot];
-      const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
-      if (STATS) cnt.chords += looked;
-      if (h.leaf >= 0) best_slot = last_slot;
-    }
+    if (there && test_entry<SMEM, PORTALS, STATS, CUT>(ac, (int)sl.run[last_slot], ox, oy, dx, dy, h, cnt)) best_slot = last_slot;
   }
 #pragma unroll
   for (int k = 0; k < W; ++k) rest |= m[k];
@@ -278,16 +302,12 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const Slots& sl, u
           open = false;
           break;
         }
-        const int run = (int)sl.run[slot];
-        const float4 b = LOCAL ? sl.box[slot] : ac.run_box[run];
+        const int entry = (int)sl.run[slot];
+        const float4 b = LOCAL ? sl.box[slot] : ac.slot_box[entry];
         float te;
         const float tn = slab_enter(sr, b, &te);
         if (STATS) cnt.nodes++;
-        if (tn <= te && tn <= h.t * RDC_CULL_SLACK) {
-          const int looked = test_run<SMEM, PORTALS>(ac.runs + (size_t)run * kRunVec, run, ox, oy, dx, dy, 1.0f, 1u, 0u, h);
-          if (STATS) cnt.chords += looked;
-          if (h.leaf == run) best_slot = slot;
-        }
+        if (tn <= te && tn <= h.t * RDC_CULL_SLACK && test_entry<SMEM, PORTALS, STATS, CUT>(ac, entry, ox, oy, dx, dy, h, cnt)) best_slot = slot;
       }
     }
   }
@@ -303,9 +323,10 @@ __device__ __forceinline__ Hit table_closest(const Accel& ac, const Slots& sl, u
 // than this can be the answer (a deferred ray of the local table already has a candidate).
 template <bool SMEM, bool PORTALS, bool STATS>
 __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float ox, float oy, float dx, float dy,
-                                             bool primary, uint32_t skip_lo, uint32_t skip_hi, float bound, Counters& cnt) {
+                                             bool primary, uint32_t skip_lo, uint32_t skip_hi, float bound, Counters& cnt,
+                                             int root, bool whole_ray) {
   Hit h;
-  if (STATS) cnt.rays++;
+  if (STATS && whole_ray) cnt.rays++;  // (a walk below one table entry is part of a ray the table already counted)
   h.t = bound;  // +inf, or the distance of a hit already known (that hit is found again: ties go to the smaller id)
   h.s = 0.0f;
   h.leaf = -1;
@@ -320,7 +341,7 @@ __device__ __forceinline__ Hit closest_chord(const Accel& ac, bool brute, float 
   const SlabRay sr = slab_ray(ox, oy, dx, dy);
   int2 stack[kStack];  // (node, entry distance bits)
   int sp = 0;
-  int node = 0;
+  int node = root;
   // while-while form (Aila & Laine 2009): every lane first walks inner nodes until it stands on a leaf (or has nothing
   // left), then the warp tests leaves together — a lane on a leaf no longer waits out its neighbours' node steps one
   // iteration at a time, and vice versa. Same visits in the same order per lane as the single if/else loop it replaces:
@@ -800,7 +821,7 @@ __device__ __forceinline__ LocalInfo gather_local(const Accel& ac, float ox0, fl
 
 template <bool SMEM, bool PORTALS, bool STATS, int MODE>
 __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderArgs a) {
-  constexpr bool TABLE = MODE == kModeTable, LOCAL = MODE == kModeLocal;
+  constexpr bool CUT = MODE == kModeCut, TABLE = MODE == kModeTable || CUT, LOCAL = MODE == kModeLocal;
   extern __shared__ uint4 smem[];
   Accel ac;
   ac.n_runs = a.sc.n_runs;
@@ -819,19 +840,33 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     ac.runs = reinterpret_cast<const float4*>(smem + node_words);
     ac.run_box = a.sc.run_box;
     smem_words = node_words + run_words;
-    if (TABLE) {
+    if (TABLE && !CUT) {
       const uint4* gb = reinterpret_cast<const uint4*>(a.sc.run_box);
 #pragma unroll 1
       for (uint32_t i = threadIdx.x; i < a.sc.n_runs; i += kBlock) smem[smem_words + i] = __ldg(gb + i);
       ac.run_box = reinterpret_cast<const float4*>(smem + smem_words);
       smem_words += a.sc.n_runs;
     }
-    __syncthreads();
   } else {
     ac.nodes = a.sc.nodes;
     ac.runs = reinterpret_cast<const float4*>(a.sc.runs);
     ac.run_box = a.sc.run_box;
   }
+  ac.slot_box = ac.run_box;  // whole-scene table: entry = run
+  ac.slot_node = nullptr;
+  if (CUT) {
+    // cut mode: the table's entries (boxes, and what each stands for) always live in shared memory — 64 x 20 bytes
+    const uint4* gb = reinterpret_cast<const uint4*>(a.sc.cut_box);
+    int* nodes_at = reinterpret_cast<int*>(smem + smem_words + kTableRuns);
+    if (threadIdx.x < a.sc.n_cut) {
+      smem[smem_words + threadIdx.x] = __ldg(gb + threadIdx.x);
+      nodes_at[threadIdx.x] = __ldg(a.sc.cut_node + threadIdx.x);
+    }
+    ac.slot_box = reinterpret_cast<const float4*>(smem + smem_words);
+    ac.slot_node = nodes_at;
+    smem_words += kTableRuns + kTableRuns / 4;
+  }
+  if (SMEM || CUT) __syncthreads();
   // local table: one WarpLocal per warp behind the staged scene
   WarpLocal* const wl = LOCAL ? reinterpret_cast<WarpLocal*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
   // whole-scene table: one WarpOrder per warp behind the staged scene
@@ -916,7 +951,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       const float jit = a.use_aa ? fabsf(a.zoom) : 0.0f;
       const float ox0 = fminf(xa, xb) - jit, ox1 = fmaxf(xa, xb) + jit, oy0 = fminf(ya, yb) - jit, oy1 = fmaxf(ya, yb) + jit;
       const int n = a.n_iter, split = (int)a.split, shift = 31 - __clz(split);
-      uint32_t n_slots = ac.n_runs;
+      uint32_t n_slots = CUT ? a.sc.n_cut : ac.n_runs;
       float settle_below = inf;  // local table: a hit closer than this is final
       bool complete = true;      // the table holds every run: a miss is final, too
       int first_root = 0, span_root = -1;  // local table: the rays that can reach the scene at all
@@ -947,7 +982,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           const uint32_t r = lane + 32u * k;
           key[k] = 0xFFFFFFFFu;
           if (r < n_slots) {  // gaps are >= 0: their bit patterns sort like the values; the run in the low bits makes keys unique
-            key[k] = (__float_as_uint(box_gap(ac.run_box[r], ox0, ox1, oy0, oy1)) & ~0x3Fu) | r;
+            key[k] = (__float_as_uint(box_gap(ac.slot_box[r], ox0, ox1, oy0, oy1)) & ~0x3Fu) | r;
             wo->key[r] = key[k];
           }
         }
@@ -973,7 +1008,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       for (int k = 0; k < W; ++k) {
         first[k] = 0; span[k] = -1;
         if (lane + 32u * k < n_slots &&
-            !angular_interval(LOCAL ? wl->box[lane + 32 * k] : ac.run_box[wo->run[lane + 32 * k]], ox0, ox1, oy0, oy1, n, first[k], span[k])) {
+            !angular_interval(LOCAL ? wl->box[lane + 32 * k] : ac.slot_box[wo->run[lane + 32 * k]], ox0, ox1, oy0, oy1, n, first[k], span[k])) {
           first[k] = 0; span[k] = n - 1;
         }
         if (LOCAL) {
@@ -1094,7 +1129,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           gen_ray(a, pixel, base_x, base_y, i, small_angle, ox, oy, dx, dy);
           Hit h;
           if (!LOCAL || m_any != 0u) {
-            h = table_closest<SMEM, PORTALS, STATS, LOCAL, W>(ac, sl, m, last_slot, ox, oy, dx, dy, cnt);
+            h = table_closest<SMEM, PORTALS, STATS, LOCAL, CUT, W>(ac, sl, m, last_slot, ox, oy, dx, dy, cnt);
           } else {
             h.t = inf; h.s = 0.0f; h.leaf = -1; h.j = 0; h.id = kMiss;
           }
@@ -1279,7 +1314,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
 // Everything about a launch that follows from the scene and the frame parameters alone.
 struct LaunchPlan {
   int n_iter = 0;
-  bool smem = false, portals = false, table = false, local = false;
+  bool smem = false, portals = false, table = false, local = false, cut = false;
   float local_r0 = 0.0f;
   size_t dyn = 0;
   int variant = 0;
@@ -1308,7 +1343,7 @@ int check_params(const rdc_frame_params& p) {
     set_error("render: more than 2^32 pixels");
     return RDC_E_LIMIT;
   }
-  if (p.route < RDC_ROUTE_AUTO || p.route > RDC_ROUTE_LOCAL_TABLE) {
+  if (p.route < RDC_ROUTE_AUTO || p.route > RDC_ROUTE_CUT_TABLE) {
     set_error("render: unknown route %d", p.route);
     return RDC_E_INVALID;
   }
@@ -1360,10 +1395,19 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
     }
   }
   if (L.local && p.local_radius > 0.0f) L.local_r0 = p.local_radius;
+  //  * a table per tile over a CUT through the tree — at most 64 subtrees and leaves that together hold every run, nearest
+  //    first, each walked only when the ray's stratum and the slab test let it: scenes of 65 runs and more that have a
+  //    surface-area tree (accel.cu) and do not take the local run table
+  L.cut = masks_ok && !L.table && !L.local && s->dev.n_cut > 0 && (p.route == RDC_ROUTE_AUTO || p.route == RDC_ROUTE_CUT_TABLE);
+  if (p.route == RDC_ROUTE_CUT_TABLE && masks_ok && !L.table && s->dev.n_cut > 0) {
+    L.cut = true;
+    L.local = false;
+  }
   L.dyn = (L.smem ? scene_bytes + (L.table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
-          (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0) + (L.table ? (size_t)(kBlock / 32) * sizeof(WarpOrder) : 0);
-  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table
-  L.variant = (L.smem ? 1 : 0) | ((L.portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (L.table ? 8 : 0) | (L.local ? 16 : 0);
+          (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0) + ((L.table || L.cut) ? (size_t)(kBlock / 32) * sizeof(WarpOrder) : 0) +
+          (L.cut ? (size_t)(kTableRuns + kTableRuns / 4) * 16 : 0);
+  // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table, bit 5 cut table
+  L.variant = (L.smem ? 1 : 0) | ((L.portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (L.table ? 8 : 0) | (L.local ? 16 : 0) | (L.cut ? 32 : 0);
   // Units per tile: how many work units a tile's rays are dealt to (unit q traces rays i = q mod split; the units' partial
   // sums are added in unit order). More units balance a launch better, fewer cost less: every unit pays for its run table
   // and its partial sums, and the rays of a unit lie `split` strata apart, which makes the previous ray's hit a worse
@@ -1380,7 +1424,7 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   L.local_tiles = tiles_x * ((L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH);
   const uint64_t warps = (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) * RDC_MIN_BLOCKS * (kBlock / 32);
   uint32_t split = 1;
-  const uint64_t units_per_warp = L.table ? 12ull : 48ull;
+  const uint64_t units_per_warp = L.table ? 12ull : 48ull;  // (cut tables walk subtrees: their units are as long as the tree's)
   while (split < (uint32_t)kAutoSplit && (uint64_t)L.local_tiles * split < units_per_warp * warps) split <<= 1;
   if (p.units_per_tile) split = p.units_per_tile;
   // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
@@ -1412,6 +1456,12 @@ int prepare_variant(rdc_scene* s, const LaunchPlan& L, RenderKernel* out) {
     case 19: kernel = k_render<true, true, false, kModeLocal>; break;
     case 22: kernel = k_render<false, true, true, kModeLocal>; break;
     case 23: kernel = k_render<true, true, true, kModeLocal>; break;
+    case 32: kernel = k_render<false, false, false, kModeCut>; break;
+    case 33: kernel = k_render<true, false, false, kModeCut>; break;
+    case 34: kernel = k_render<false, true, false, kModeCut>; break;
+    case 35: kernel = k_render<true, true, false, kModeCut>; break;
+    case 38: kernel = k_render<false, true, true, kModeCut>; break;
+    case 39: kernel = k_render<true, true, true, kModeCut>; break;
     default:
       set_error("render: no kernel variant %d", variant);
       return RDC_E_INVALID;

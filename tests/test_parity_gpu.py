@@ -153,6 +153,8 @@ def test_tree_builders_give_the_same_frame(name, xml_dir, api, port_oracle):
         for route in (api.ROUTE_TREE, api.ROUTE_AUTO):
             out = r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, route=route), want_hits=True, want_stats=True)
             assert np.array_equal(out["hits"], ohits), (tree, route)
+            plain = r.render(api.default_frame_params(w, h, n, zoom_factor=zoom, route=route), want_hits=True)
+            assert np.array_equal(plain["hits"], ohits), (tree, route, "plain build")
             compare_images(out["image"], oimg, RGB_TOL)
             outs[(tree, route)] = out["image"]
             boxes[(tree, route)] = out["stats"][1]
@@ -161,6 +163,38 @@ def test_tree_builders_give_the_same_frame(name, xml_dir, api, port_oracle):
     print(f"{name}: boxes tested on the tree route: Morton {boxes[(api.TREE_MORTON, api.ROUTE_TREE)]}, SAH {boxes[(api.TREE_SAH, api.ROUTE_TREE)]}")
     with pytest.raises(api.RdcError):
         GpuRenderer(path, accel=api.default_accel_options(tree=7))
+
+
+CUT_VIEWS = [("DiffusionCurvePack/lady_bug.xml", 512 / 52, 0.0, 0.0, 16, 2), ("DiffusionCurvePack/lady_bug.xml", 1.0, -30.0, 20.0, 24, 2),
+             ("DiffusionCurvePack/face.xml", 0.3, -20.0, 35.0, 40, 2), ("DiffusionCurvePack/dolphin.xml", 633 / 52, 0.0, 0.0, 16, 2),
+             ("DiffusionCurvePack/dolphin.xml", 0.5, 60.0, -40.0, 16, 2), ("test4.xml", 512 / 52, 0.0, 0.0, 32, 2),
+             ("PortalDemo.xml", 3.0, 10.0, -5.0, 16, 31)]
+
+
+@pytest.mark.parametrize("name,zoom,off_x,off_y,n,depth", CUT_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[1]:.2f}" for v in CUT_VIEWS])
+def test_cut_table_views(name, zoom, off_x, off_y, n, depth, xml_dir, api, port_oracle):
+    """The per-tile table over a 64-entry cut through the tree (mid-size scenes): entries are subtrees or leaves, nearest
+    first; every first hit still the oracle's brute-force closest chord, whole frames and frames cut in bands alike."""
+    path = os.path.join(xml_dir, name)
+    scene = po.ingest_xml(path, True)
+    w, h = 72, 52
+    kw = dict(zoom_factor=zoom, offset_x=off_x, offset_y=off_y, max_trace_depth=depth)
+    oimg, oblur, ohits = port_oracle.render(scene, po.make_params(w, h, n, **kw), want_hits=True, search="grid")
+    r = GpuRenderer(path, accel=api.default_accel_options(tree=api.TREE_SAH))
+    forced = r.scene.stats.n_runs > 64
+    route = api.ROUTE_CUT_TABLE if forced else api.ROUTE_AUTO
+    out = r.render(api.default_frame_params(w, h, n, route=route, **kw), want_hits=True)
+    assert np.array_equal(out["hits"], ohits)
+    compare_images(out["image"], oimg, RGB_TOL)
+    counted = r.render(api.default_frame_params(w, h, n, route=route, **kw), want_hits=True, want_stats=True)
+    assert np.array_equal(counted["hits"], ohits)
+    tree = r.render(api.default_frame_params(w, h, n, route=api.ROUTE_TREE, **kw), want_hits=True, want_stats=True)
+    assert np.array_equal(tree["hits"], ohits)
+    if forced:
+        assert counted["stats"][0] <= tree["stats"][0], "the table traces no more rays than the per-pixel cull lets through"
+    parts = [r.render(api.default_frame_params(w, h, n, route=route, row_begin=b, row_end=e, **kw))["image"] for b, e in ((0, 20), (20, 52))]
+    assert np.array_equal(bits(np.concatenate(parts)), bits(out["image"]))
+    print(f"{name} zoom {zoom:.2f}: rays traced {counted['stats'][0]} (tree route {tree['stats'][0]}), boxes {counted['stats'][1]} ({tree['stats'][1]})")
 
 
 def test_row_bands_concatenate_bit_exactly(xml_dir, api):

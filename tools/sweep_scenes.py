@@ -59,6 +59,7 @@ def main():
         if modes:
             row["tree_render_ms"] = round(time_frames(scene, width, height, rpp, zoom, route=api.ROUTE_TREE)[0], 3)
             row["local_render_ms"] = round(time_frames(scene, width, height, rpp, zoom, route=api.ROUTE_LOCAL_TABLE)[0], 3)
+            row["cut_render_ms"] = round(time_frames(scene, width, height, rpp, zoom, route=api.ROUTE_CUT_TABLE)[0], 3)
         total += render_ms + blur_ms
         rows.append(row)
         print(json.dumps(row), flush=True)
