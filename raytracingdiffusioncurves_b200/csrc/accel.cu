@@ -850,7 +850,7 @@ int build_scene(const rdc_scene_arrays& a, const rdc_accel_options& o, cudaStrea
         TEMP_CUDA(cudaMemcpyAsync(nodes, h_nodes.data(), h_nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, stream));
         std::vector<int> cut_entry;
         std::vector<float4> cut_boxes;
-        tree_cut(h_nodes, (int)n_runs, 64, cut_entry, cut_boxes);
+        tree_cut(h_nodes, (int)n_runs, RDC_CUT_SEED, cut_entry, cut_boxes);
         d.cut_node = up.upload(cut_entry.data(), cut_entry.size());
         d.cut_box = up.upload(cut_boxes.data(), cut_boxes.size());
         d.n_cut = (uint32_t)cut_entry.size();

@@ -41,6 +41,9 @@ struct __align__(16) SegWalk {
   uint32_t pad0, pad1;
 };
 
+// entries of the scene-wide seed cut through the tree (cut_node / cut_box below); the render kernel opens it further per tile
+#define RDC_CUT_SEED 32
+
 struct DevStops {
   const uint2* index;  // {start,count} per curve
   const float* u;      // flat stop parameters (+INF sentinels at the end)
@@ -77,8 +80,8 @@ struct DevScene {
   const uint4* run_ids;            // [n_runs] Morton order: first chord id, segment, k of the first chord, K
   const float4* run_box;           // [n_runs] Morton order: padded box of each run (per-tile run table)
   const BvhNode* nodes;            // [max(n_runs-1,1)]
-  // cut through the tree: at most 64 subtrees (node index) or leaves (~run) that together hold every run, with their padded
-  // boxes — the slots of the per-tile table of mid-size scenes (render.cu, kModeCut). n_cut == 0: no cut (Morton trees).
+  // seed cut through the tree: at most RDC_CUT_SEED subtrees (node index) or leaves (~run) that together hold every run, with
+  // their padded boxes — what the per-tile cut table starts from (render.cu, kModeCut). n_cut == 0: no cut (Morton trees).
   const int* cut_node;
   const float4* cut_box;
   uint32_t n_cut;

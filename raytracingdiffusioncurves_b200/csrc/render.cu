@@ -78,6 +78,15 @@ struct __align__(16) WarpOrder {
 };
 static_assert(kTableRuns <= 64, "sort keys carry the run in their low six bits");
 
+// cut table: the warp's own cut through the tree for the tile in work — the scene's seed cut (accel.cu) with the subtrees
+// nearest the tile opened until the table is full — followed by its WarpOrder
+struct __align__(16) WarpCut {
+  float4 box[kTableRuns];  // padded box of each entry
+  int node[kTableRuns];    // what the entry is: node index (subtree) or ~run (leaf)
+  WarpOrder order;
+};
+static_assert(RDC_CUT_SEED <= kTableRuns, "the seed cut must fit the table");
+
 struct RenderArgs {
   DevScene sc;
   float4* image;
@@ -854,23 +863,16 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   }
   ac.slot_box = ac.run_box;  // whole-scene table: entry = run
   ac.slot_node = nullptr;
-  if (CUT) {
-    // cut mode: the table's entries (boxes, and what each stands for) always live in shared memory — 64 x 20 bytes
-    const uint4* gb = reinterpret_cast<const uint4*>(a.sc.cut_box);
-    int* nodes_at = reinterpret_cast<int*>(smem + smem_words + kTableRuns);
-    if (threadIdx.x < a.sc.n_cut) {
-      smem[smem_words + threadIdx.x] = __ldg(gb + threadIdx.x);
-      nodes_at[threadIdx.x] = __ldg(a.sc.cut_node + threadIdx.x);
-    }
-    ac.slot_box = reinterpret_cast<const float4*>(smem + smem_words);
-    ac.slot_node = nodes_at;
-    smem_words += kTableRuns + kTableRuns / 4;
-  }
-  if (SMEM || CUT) __syncthreads();
+  if (SMEM) __syncthreads();
   // local table: one WarpLocal per warp behind the staged scene
   WarpLocal* const wl = LOCAL ? reinterpret_cast<WarpLocal*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
   // whole-scene table: one WarpOrder per warp behind the staged scene
-  WarpOrder* const wo = TABLE ? reinterpret_cast<WarpOrder*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
+  WarpCut* const wc = CUT ? reinterpret_cast<WarpCut*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
+  WarpOrder* const wo = CUT ? &wc->order : TABLE ? reinterpret_cast<WarpOrder*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
+  if (CUT) {  // cut mode: table entries are the warp's own
+    ac.slot_box = wc->box;
+    ac.slot_node = wc->node;
+  }
 
   // Persistent warps: every warp of the (SM-filling) grid keeps fetching work units from one global
   // counter until the image is done. A tile is 8x4 pixels, one lane per pixel, all lanes on the same ray
@@ -971,6 +973,47 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         }
       }
       constexpr int W = LOCAL ? kLocalWords : kTableWords;  // lane L looks after slots L, L+32, ...
+      if (CUT) {
+        // Cut table: start from the scene's seed cut and open the subtree nearest the tile, again and again, until the table
+        // is full or only leaves are left. Near the tile the entries end up as single runs (tested directly, like the
+        // whole-scene table's), far away they stay whole subtrees: the table is complete at any scene size and as fine as it
+        // needs to be where most rays end. A function of the tile and the scene only, like everything in the set-up.
+        if (lane < a.sc.n_cut) {
+          wc->box[lane] = __ldg(a.sc.cut_box + lane);
+          wc->node[lane] = __ldg(a.sc.cut_node + lane);
+        }
+        if (lane + 32u < a.sc.n_cut) {
+          wc->box[lane + 32] = __ldg(a.sc.cut_box + lane + 32);
+          wc->node[lane + 32] = __ldg(a.sc.cut_node + lane + 32);
+        }
+        n_slots = a.sc.n_cut;
+        __syncwarp();
+#pragma unroll 1
+        while (n_slots < kTableRuns) {
+          uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+          for (int k = 0; k < kTableWords; ++k) {
+            const uint32_t e = lane + 32u * k;
+            if (e < n_slots && wc->node[e] >= 0)
+              best = min(best, (__float_as_uint(box_gap(wc->box[e], ox0, ox1, oy0, oy1)) & ~0x3Fu) | e);
+          }
+          best = __reduce_min_sync(0xFFFFFFFFu, best);
+          if (best == 0xFFFFFFFFu) break;  // only leaves left
+          const uint32_t e = best & 0x3Fu;
+          const float4* np = reinterpret_cast<const float4*>(ac.nodes + wc->node[e]);
+          const float4 lb = load16<SMEM>(np), rb = load16<SMEM>(np + 1), ch = load16<SMEM>(np + 2);
+          if (STATS && lane == 0) cnt.gathered++;
+          __syncwarp();  // every lane has read the entry that is about to be replaced
+          if (lane == 0) {
+            wc->box[e] = lb;
+            wc->node[e] = __float_as_int(ch.x);
+            wc->box[n_slots] = rb;
+            wc->node[n_slots] = __float_as_int(ch.y);
+          }
+          n_slots++;
+          __syncwarp();
+        }
+      }
       if (TABLE) {
         // Whole-scene table: put the runs in order of their distance from the tile (all-pairs ranking of at most 64 keys,
         // once per unit). A ray's candidates then come nearest first and its scan stops at the first slot beyond its hit:
@@ -1369,7 +1412,9 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   L.local_rows = L.strip_stride > 1 ? my_strips * kStripRows : rows;
   L.row_skew = L.strip_stride > 1 ? 0u : p.row_begin % kWarpTileH;  // strips: give row_begin as a multiple of 4 for split-independent bits
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
-  L.smem = scene_bytes <= kSmemSceneLimit;
+  // nodes + runs are staged in shared memory when four blocks per SM still fit next to the per-warp tables
+  const bool cut_capable = s->dev.n_cut > 0 && s->dev.n_runs > kTableRuns;
+  L.smem = scene_bytes + (cut_capable ? (size_t)(kBlock / 32) * sizeof(WarpCut) : 0) <= kSmemSceneLimit;
   L.portals = s->info.has_portals != 0;
   const bool brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
   // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
@@ -1403,8 +1448,8 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   }
   if (L.local && p.local_radius > 0.0f) L.local_r0 = p.local_radius;
   L.dyn = (L.smem ? scene_bytes + (L.table ? (size_t)s->dev.n_runs * sizeof(float4) : 0) : 0) +
-          (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0) + ((L.table || L.cut) ? (size_t)(kBlock / 32) * sizeof(WarpOrder) : 0) +
-          (L.cut ? (size_t)(kTableRuns + kTableRuns / 4) * 16 : 0);
+          (L.local ? (size_t)(kBlock / 32) * sizeof(WarpLocal) : 0) + (L.table ? (size_t)(kBlock / 32) * sizeof(WarpOrder) : 0) +
+          (L.cut ? (size_t)(kBlock / 32) * sizeof(WarpCut) : 0);
   // kernel variant: bit 0 shared-memory staging, bit 1 portals, bit 2 counting build, bit 3 whole-scene table, bit 4 local table, bit 5 cut table
   L.variant = (L.smem ? 1 : 0) | ((L.portals || p.stats) ? 2 : 0) | (p.stats ? 4 : 0) | (L.table ? 8 : 0) | (L.local ? 16 : 0) | (L.cut ? 32 : 0);
   // Units per tile: how many work units a tile's rays are dealt to (unit q traces rays i = q mod split; the units' partial
