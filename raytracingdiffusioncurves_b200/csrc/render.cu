@@ -1459,8 +1459,10 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   // headline frame and on a rank's share of it at 2, 4 and 8 GPUs (profiles/r02c/timeline.log): the fastest choice is the
   // one that leaves a warp about 13 units — 1 unit per tile for the whole 1080p frame (1.606 ms against 1.747 at 4), 2 for
   // half of it, 4 for a quarter or less. So: the smallest count that gives this LAUNCH at least 12 units per resident warp
-  // when the whole scene sits in the run table — and at least 48 on the tree and the local run table, whose units trace
-  // most of their rays and last several times longer (lady_bug.xml 1080p: 7.70 ms at 4 units per tile, 9.47 ms at 1).
+  // when the whole scene sits in the run table; at least 48 on the tree and the local run table, whose units trace most of
+  // their rays and last several times longer (lady_bug.xml 1080p on the tree: 7.70 ms at 4 units per tile, 9.47 ms at 1);
+  // and only 3 on the cut table, whose units each refine the cut around their tile before the first ray (lady_bug.xml 1080p:
+  // 5.16 ms at 1 unit per tile, 6.92 at 4; a rank of 8: 0.94 ms at 2, 1.12 at 8 — profiles/r02k/units.log).
   // The count is part of a pixel's summation order: launches that must agree bit for bit (a frame rendered whole and in
   // parts) pin rdc_frame_params::units_per_tile; hit indices never depend on it.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
@@ -1468,7 +1470,7 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   L.local_tiles = tiles_x * ((L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH);
   const uint64_t warps = (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) * RDC_MIN_BLOCKS * (kBlock / 32);
   uint32_t split = 1;
-  const uint64_t units_per_warp = L.table ? 12ull : 48ull;  // (cut tables walk subtrees: their units are as long as the tree's)
+  const uint64_t units_per_warp = L.table ? 12ull : L.cut ? 3ull : 48ull;
   while (split < (uint32_t)kAutoSplit && (uint64_t)L.local_tiles * split < units_per_warp * warps) split <<= 1;
   if (p.units_per_tile) split = p.units_per_tile;
   // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
