@@ -105,7 +105,8 @@ struct rdc_scene {
   cudaEvent_t launched = nullptr;
   cudaStream_t launched_on = nullptr;
   bool launched_any = false;
-  uint32_t grid_blocks[64] = {};  // SM-filling grid size per kernel variant
+  uint32_t grid_blocks[64] = {};  // SM-filling grid size per kernel variant ...
+  size_t grid_dyn[64] = {};       // ... at this much dynamic shared memory
   float mean_run_w = 0.0f, mean_run_h = 0.0f;  // mean padded run box (local-table radius estimate)
   // partial sums of k_render's work units (a tile's rays are dealt to several units), grown on demand
   float4* part_rgbw = nullptr;

@@ -87,6 +87,14 @@ struct __align__(16) WarpCut {
 };
 static_assert(RDC_CUT_SEED <= kTableRuns, "the seed cut must fit the table");
 
+// group mode (table launches with one unit per warp of a block): what the eight warps that share a tile share
+struct __align__(16) GroupShared {
+  float4 part_rgbw[kBlock / 32][32];  // the units' partial sums, added up by warp 0 in unit order
+  float part_blur[kBlock / 32][32];
+  int first[kTableRuns], span[kTableRuns];  // ray-index interval of every table slot (computed once, by warp 0)
+  uint32_t tile, n_slots;
+};
+
 struct RenderArgs {
   DevScene sc;
   float4* image;
@@ -100,6 +108,8 @@ struct RenderArgs {
   uint32_t local_rows;                  // rows of the output buffers this launch covers
   uint32_t row_skew;                    // row_begin % 4 of a contiguous band: tiles stay aligned to the full frame's
   uint32_t split;                       // work units per tile: unit q traces rays i = q (mod split)
+  int group;                            // table launches with split == warps per block: a block's warps take the units of ONE
+                                        // tile together (one table per tile instead of one per unit, partial sums in shared memory)
   uint32_t mid_tx, mid_ty;              // the tile (column, local tile row) nearest the scene's centre: units are handed out
                                         // centre-out from it
   float4* part_rgbw;                    // [split][local pixels] partial sums of units (split > 1)
@@ -867,8 +877,15 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   // local table: one WarpLocal per warp behind the staged scene
   WarpLocal* const wl = LOCAL ? reinterpret_cast<WarpLocal*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
   // whole-scene table: one WarpOrder per warp behind the staged scene
-  WarpCut* const wc = CUT ? reinterpret_cast<WarpCut*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
-  WarpOrder* const wo = CUT ? &wc->order : TABLE ? reinterpret_cast<WarpOrder*>(smem + smem_words) + (threadIdx.x >> 5) : nullptr;
+  // Group mode: the eight warps of a block work on the eight units of one tile. The tile's table (order, cut, slot
+  // intervals) is made once, by warp 0, in warp 0's slot of the per-warp tables; everybody reads it from there.
+  const uint32_t warp = threadIdx.x >> 5;
+  const bool group = TABLE && a.group != 0;
+  const uint32_t table_of = group ? 0u : warp;
+  WarpCut* const wc = CUT ? reinterpret_cast<WarpCut*>(smem + smem_words) + table_of : nullptr;
+  WarpOrder* const wo = CUT ? &wc->order : TABLE ? reinterpret_cast<WarpOrder*>(smem + smem_words) + table_of : nullptr;
+  GroupShared* const gs = group ? reinterpret_cast<GroupShared*>(smem + smem_words + (kBlock / 32) * (CUT ? sizeof(WarpCut) : sizeof(WarpOrder)) / 16)
+                                : nullptr;
   if (CUT) {  // cut mode: table entries are the warp's own
     ac.slot_box = wc->box;
     ac.slot_node = wc->node;
@@ -901,14 +918,22 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   }
   for (;;) {
     uint32_t unit = 0;
-    if (lane == 0) unit = atomicAdd(a.work, 1u);
-    unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
-    if (unit >= n_units) break;
+    if (group) {
+      __syncthreads();  // the previous tile is finished with: its table and partial sums may be overwritten
+      if (threadIdx.x == 0) gs->tile = atomicAdd(a.work, 1u);
+      __syncthreads();
+      unit = gs->tile;  // (a tile, not a unit: the unit is the warp's number)
+      if (unit >= n_units / a.split) break;
+    } else {
+      if (lane == 0) unit = atomicAdd(a.work, 1u);
+      unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
+      if (unit >= n_units) break;
+    }
     // Units are handed out centre-out from the tile nearest the scene's centre, dearest first: a tile that looks at the scene
     // from close by traces several times the rays of one far away, and a launch ends when its last unit does — with the long
     // units up front the tail is made of short ones (a rank of 8 has 3.4 units per warp at 1080p: 0.264 ms where 0.221 is
     // the mean). Which warp renders a tile when has no bearing on its pixels.
-    const uint32_t ord = unit / a.split, q = unit % a.split;
+    const uint32_t ord = group ? unit : unit / a.split, q = group ? warp : unit % a.split;
     const uint32_t tile = centre_out(ord / tiles_x, a.mid_ty, n_tile_rows) * tiles_x + centre_out(ord % tiles_x, a.mid_tx, tiles_x);
     const uint32_t ix = (tile % tiles_x) * kWarpTileW + lane % kWarpTileW;
     const uint32_t vy = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local) + skew
@@ -973,7 +998,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         }
       }
       constexpr int W = LOCAL ? kLocalWords : kTableWords;  // lane L looks after slots L, L+32, ...
-      if (CUT) {
+      const bool makes_table = !group || warp == 0;
+      if (CUT && makes_table) {
         // Cut table: start from the scene's seed cut and open the subtree nearest the tile, again and again, until the table
         // is full or only leaves are left. Near the tile the entries end up as single runs (tested directly, like the
         // whole-scene table's), far away they stay whole subtrees: the table is complete at any scene size and as fine as it
@@ -1014,7 +1040,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           __syncwarp();
         }
       }
-      if (TABLE) {
+      if (TABLE && makes_table) {
         // Whole-scene table: put the runs in order of their distance from the tile (all-pairs ranking of at most 64 keys,
         // once per unit). A ray's candidates then come nearest first and its scan stops at the first slot beyond its hit:
         // 0.41 boxes tested per ray instead of 0.77 on the headline frame.
@@ -1050,7 +1076,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
 #pragma unroll
       for (int k = 0; k < W; ++k) {
         first[k] = 0; span[k] = -1;
-        if (lane + 32u * k < n_slots &&
+        if (makes_table && lane + 32u * k < n_slots &&
             !angular_interval(LOCAL ? wl->box[lane + 32 * k] : ac.slot_box[wo->run[lane + 32 * k]], ox0, ox1, oy0, oy1, n, first[k], span[k])) {
           first[k] = 0; span[k] = n - 1;
         }
@@ -1058,6 +1084,23 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           wl->first[k][lane] = first[k];
           wl->span[k][lane] = span[k];
         }
+      }
+      if (TABLE && group) {  // warp 0 made the table: hand the slots' intervals (and the slot count) to the other seven
+        if (warp == 0) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            gs->first[lane + 32 * k] = first[k];
+            gs->span[lane + 32 * k] = span[k];
+          }
+          if (lane == 0) gs->n_slots = n_slots;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          first[k] = gs->first[lane + 32 * k];
+          span[k] = gs->span[lane + 32 * k];
+        }
+        n_slots = gs->n_slots;
       }
       int last_slot = -1;       // the slot this lane's previous ray hit
       uint32_t queued = 0;      // deferred rays waiting in wl->ring
@@ -1260,7 +1303,25 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
       }
     }
     bool finish = true;
-    if (a.split > 1) {
+    if (group) {
+      // the tile's eight units end together: partial sums meet in shared memory and warp 0 adds them in unit order — the
+      // order of the path below, so a pixel's bits do not depend on which of the two ran
+      gs->part_rgbw[q][lane] = make_float4(cr, cg, cb, weight_total);
+      gs->part_blur[q][lane] = blur;
+      __syncthreads();
+      finish = warp == 0;
+      if (finish) {
+        const float4 p0 = gs->part_rgbw[0][lane];
+        cr = p0.x; cg = p0.y; cb = p0.z; weight_total = p0.w;
+        blur = gs->part_blur[0][lane];
+#pragma unroll 1
+        for (uint32_t k = 1; k < a.split; ++k) {
+          const float4 pk = gs->part_rgbw[k][lane];
+          cr += pk.x; cg += pk.y; cb += pk.z; weight_total += pk.w;
+          blur += gs->part_blur[k][lane];
+        }
+      }
+    } else if (a.split > 1) {
       if (valid) {
         a.part_rgbw[q * part_stride + local_pixel] = make_float4(cr, cg, cb, weight_total);
         a.part_blur[q * part_stride + local_pixel] = blur;
@@ -1357,7 +1418,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
 // Everything about a launch that follows from the scene and the frame parameters alone.
 struct LaunchPlan {
   int n_iter = 0;
-  bool smem = false, portals = false, table = false, local = false, cut = false;
+  bool smem = false, portals = false, table = false, local = false, cut = false, group = false;
   float local_r0 = 0.0f;
   size_t dyn = 0;
   int variant = 0;
@@ -1414,7 +1475,7 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   const size_t scene_bytes = (size_t)s->dev.n_nodes * sizeof(BvhNode) + (size_t)s->dev.n_runs * sizeof(RunRecord);
   // nodes + runs are staged in shared memory when four blocks per SM still fit next to the per-warp tables
   const bool cut_capable = s->dev.n_cut > 0 && s->dev.n_runs > kTableRuns;
-  L.smem = scene_bytes + (cut_capable ? (size_t)(kBlock / 32) * sizeof(WarpCut) : 0) <= kSmemSceneLimit;
+  L.smem = scene_bytes + (cut_capable ? (size_t)(kBlock / 32) * sizeof(WarpCut) + sizeof(GroupShared) : 0) <= kSmemSceneLimit;
   L.portals = s->info.has_portals != 0;
   const bool brute = p.traversal == RDC_TRAVERSAL_BRUTE_FORCE;
   // Run tables instead of the tree for primary rays: whole number of rays >= 8, LBVH mode.
@@ -1476,6 +1537,9 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
   while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * L.local_pixels * 20ull > (2ull << 30))) split >>= 1;
   L.split = split;
+  // eight units per tile on a table launch: the eight warps of a block take them together (one table per tile, sums in shared memory)
+  L.group = (L.table || L.cut) && split == (uint32_t)(kBlock / 32);
+  if (L.group) L.dyn += sizeof(GroupShared);
   return L;
 }
 
@@ -1512,7 +1576,7 @@ int prepare_variant(rdc_scene* s, const LaunchPlan& L, RenderKernel* out) {
       set_error("render: no kernel variant %d", variant);
       return RDC_E_INVALID;
   }
-  if (s->grid_blocks[variant] == 0) {  // SM-filling grid: resident blocks per SM x SMs, once per handle and variant
+  if (s->grid_blocks[variant] == 0 || s->grid_dyn[variant] != dyn) {  // SM-filling grid: resident blocks per SM x SMs, per handle, variant and shared-memory size
     if (dyn > 48 * 1024) RDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 0, sms = 0;
     RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn));
@@ -1522,6 +1586,7 @@ int prepare_variant(rdc_scene* s, const LaunchPlan& L, RenderKernel* out) {
       return RDC_E_LIMIT;
     }
     s->grid_blocks[variant] = (uint32_t)(per_sm * sms);
+    s->grid_dyn[variant] = dyn;
   }
   *out = kernel;
   return 0;
@@ -1538,7 +1603,7 @@ int ensure_capacity(rdc_scene* s, const LaunchPlan& L, cudaStream_t stream) {
     s->base_dirs_capacity = (uint32_t)L.n_iter;
     s->base_dirs_n = -1.0f;
   }
-  if (L.split > 1 && (L.local_pixels * L.split > s->part_capacity || L.local_tiles > s->tile_capacity)) {
+  if (L.split > 1 && !L.group && (L.local_pixels * L.split > s->part_capacity || L.local_tiles > s->tile_capacity)) {
     if (s->launched) RDC_CUDA(cudaEventSynchronize(s->launched));
     cudaFree(s->part_rgbw);
     cudaFree(s->part_blur);
@@ -1662,6 +1727,7 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const int variant = L.variant;
   const size_t dyn = L.dyn;
   a.split = L.split;
+  a.group = L.group ? 1 : 0;
   {
     // the scene's centre in pixels of the full frame (inverse of DeviceCode.cu:103-107), then in tiles of this launch
     const float4 rb = s->dev.root_box;
