@@ -136,6 +136,41 @@ def test_host_consumer_frame_equals_one_call_frame(world, name, width, height, c
         ranks.close()
 
 
+@pytest.mark.parametrize("name", ["arch.xml", "DiffusionCurvePack/lady_bug.xml"])
+def test_group_mode_through_peer_frames(name, xml_dir, api):
+    """Eight units per tile (group mode: a block's warps share a tile's table, partial sums in shared memory) with the finished
+    pixels stored into the consumers' frames: three ranks, 128 rays per pixel, the summation order pinned on both sides."""
+    import ctypes
+
+    import torch
+
+    path = os.path.join(xml_dir, name)
+    width, height, rpp, world = 96, 72, 128, 3
+    zoom = 512 / height
+    ranks = Ranks(api, path, width, height, world)
+    halo = ranks.host.halo_rows(2)
+    ranks.reserve(api.default_frame_params(width, height, rpp, zoom_factor=zoom, units_per_tile=8))
+    try:
+        ptr = 0
+        for r, scene, frames, stream in ranks.each():
+            got = frames.render_frame(scene, api.default_frame_params(width, height, rpp, zoom_factor=zoom, units_per_tile=8), True, halo, stream)
+            ptr = got if r == 0 else ptr
+        ranks.sync()
+        out = torch.empty((height, width, 4), dtype=torch.float32)
+        with torch.cuda.device(ranks.devices[0]):
+            assert ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(out.numel() * 4), 2) == 0
+        host = api.HostScene.from_xml_file(path)
+        s = torch.cuda.current_stream().cuda_stream
+        scene = api.Scene(host.arrays, None, s)
+        want = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
+        for units in (8, 4):  # group mode and the global partial sums add in the same order: the same bits
+            scene.render_frame_to_host(api.default_frame_params(width, height, rpp, zoom_factor=zoom, units_per_tile=units), True, want.data_ptr(), s)
+            if units == 8:
+                assert np.array_equal(bits(out.numpy()[..., :3]), bits(want.numpy()[..., :3]))
+    finally:
+        ranks.close()
+
+
 def test_barrier_reports_a_missing_rank(api):
     """A rank that never arrives raises the error flag after the time limit instead of wedging the GPU."""
     import torch
