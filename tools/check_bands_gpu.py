@@ -20,7 +20,7 @@ from raytracingdiffusioncurves_b200 import api, distributed as rd  # noqa: E402
 
 XML = os.path.join(ROOT, "tests", "golden", "xmls")
 CASES = [("arch.xml", 640, 360, 32), ("DiffusionCurvePack/lady_bug.xml", 512, 384, 16), ("DiffusionCurvePack/face.xml", 256, 64, 8),
-         ("PortalDemo.xml", 320, 242, 16)]
+         ("PortalDemo.xml", 320, 242, 16), ("arch.xml", 1920, 1080, 128), ("DiffusionCurvePack/lady_bug.xml", 960, 540, 128)]
 
 
 def main():
@@ -36,7 +36,9 @@ def main():
         zoom = host.arrays.image_height / h
 
         def make(frame=3, b=0, e=h):
-            return api.default_frame_params(w, h, rpp, zoom_factor=zoom, row_begin=b, row_end=e, frame=frame)
+            # units per tile pinned: the whole frame and a rank's share would otherwise pick different summation orders
+            # (8 = group mode where a launch has 128 rays per pixel; fewer rays clamp it, the same way on both sides)
+            return api.default_frame_params(w, h, rpp, zoom_factor=zoom, row_begin=b, row_end=e, frame=frame, units_per_tile=8)
 
         halo = host.halo_rows(2)
         scene.reserve(make(), False, stream)
