@@ -87,12 +87,16 @@ struct __align__(16) WarpCut {
 };
 static_assert(RDC_CUT_SEED <= kTableRuns, "the seed cut must fit the table");
 
-// group mode (table launches with one unit per warp of a block): what the eight warps that share a tile share
+// group mode (table launches with more than one unit per tile): the G warps that take a tile's G units together share ...
+struct __align__(16) GroupTable {
+  int first[kTableRuns], span[kTableRuns];  // ray-index interval of every table slot (computed once, by the group's first warp)
+  uint32_t tile, n_slots, pad0, pad1;
+};
+// ... and a block (8 / G groups) holds
 struct __align__(16) GroupShared {
-  float4 part_rgbw[kBlock / 32][32];  // the units' partial sums, added up by warp 0 in unit order
+  float4 part_rgbw[kBlock / 32][32];  // every warp's partial sums, added up by its group's first warp in unit order
   float part_blur[kBlock / 32][32];
-  int first[kTableRuns], span[kTableRuns];  // ray-index interval of every table slot (computed once, by warp 0)
-  uint32_t tile, n_slots;
+  GroupTable table[kBlock / 64];      // one per group (at most four groups of two warps)
 };
 
 struct RenderArgs {
@@ -108,8 +112,8 @@ struct RenderArgs {
   uint32_t local_rows;                  // rows of the output buffers this launch covers
   uint32_t row_skew;                    // row_begin % 4 of a contiguous band: tiles stay aligned to the full frame's
   uint32_t split;                       // work units per tile: unit q traces rays i = q (mod split)
-  int group;                            // table launches with split == warps per block: a block's warps take the units of ONE
-                                        // tile together (one table per tile instead of one per unit, partial sums in shared memory)
+  int group;                            // table launches with split > 1: G = split warps of a block take the units of ONE tile
+                                        // together (one table per tile instead of one per unit, partial sums in shared memory); 0 = off
   uint32_t mid_tx, mid_ty;              // the tile (column, local tile row) nearest the scene's centre: units are handed out
                                         // centre-out from it
   float4* part_rgbw;                    // [split][local pixels] partial sums of units (split > 1)
@@ -881,11 +885,19 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   // intervals) is made once, by warp 0, in warp 0's slot of the per-warp tables; everybody reads it from there.
   const uint32_t warp = threadIdx.x >> 5;
   const bool group = TABLE && a.group != 0;
-  const uint32_t table_of = group ? 0u : warp;
+  const uint32_t G = group ? (uint32_t)a.group : 1u;   // warps per group = units per tile (2, 4 or 8)
+  const uint32_t gid = group ? warp / G : 0u;           // this warp's group inside the block
+  const uint32_t table_of = group ? gid * G : warp;     // the group's first warp owns the tile's table
+  // the group's warps meet at a barrier of their own (a named barrier; the whole block's when the group is the block)
+  auto group_sync = [&]() {
+    if (G == (uint32_t)(kBlock / 32)) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1u + gid), "r"(32u * G) : "memory");
+  };
   WarpCut* const wc = CUT ? reinterpret_cast<WarpCut*>(smem + smem_words) + table_of : nullptr;
   WarpOrder* const wo = CUT ? &wc->order : TABLE ? reinterpret_cast<WarpOrder*>(smem + smem_words) + table_of : nullptr;
   GroupShared* const gs = group ? reinterpret_cast<GroupShared*>(smem + smem_words + (kBlock / 32) * (CUT ? sizeof(WarpCut) : sizeof(WarpOrder)) / 16)
                                 : nullptr;
+  GroupTable* const gt = group ? &gs->table[gid] : nullptr;
   if (CUT) {  // cut mode: table entries are the warp's own
     ac.slot_box = wc->box;
     ac.slot_node = wc->node;
@@ -919,10 +931,10 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
   for (;;) {
     uint32_t unit = 0;
     if (group) {
-      __syncthreads();  // the previous tile is finished with: its table and partial sums may be overwritten
-      if (threadIdx.x == 0) gs->tile = atomicAdd(a.work, 1u);
-      __syncthreads();
-      unit = gs->tile;  // (a tile, not a unit: the unit is the warp's number)
+      group_sync();  // the previous tile is finished with: its table and partial sums may be overwritten
+      if (warp == table_of && lane == 0) gt->tile = atomicAdd(a.work, 1u);
+      group_sync();
+      unit = gt->tile;  // (a tile, not a unit: the unit is the warp's number inside its group)
       if (unit >= n_units / a.split) break;
     } else {
       if (lane == 0) unit = atomicAdd(a.work, 1u);
@@ -933,7 +945,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     // from close by traces several times the rays of one far away, and a launch ends when its last unit does — with the long
     // units up front the tail is made of short ones (a rank of 8 has 3.4 units per warp at 1080p: 0.264 ms where 0.221 is
     // the mean). Which warp renders a tile when has no bearing on its pixels.
-    const uint32_t ord = group ? unit : unit / a.split, q = group ? warp : unit % a.split;
+    const uint32_t ord = group ? unit : unit / a.split, q = group ? warp - table_of : unit % a.split;
     const uint32_t tile = centre_out(ord / tiles_x, a.mid_ty, n_tile_rows) * tiles_x + centre_out(ord % tiles_x, a.mid_tx, tiles_x);
     const uint32_t ix = (tile % tiles_x) * kWarpTileW + lane % kWarpTileW;
     const uint32_t vy = (tile / tiles_x) * kWarpTileH + lane / kWarpTileW;  // row inside the output buffer (band- or strip-local) + skew
@@ -998,7 +1010,7 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
         }
       }
       constexpr int W = LOCAL ? kLocalWords : kTableWords;  // lane L looks after slots L, L+32, ...
-      const bool makes_table = !group || warp == 0;
+      const bool makes_table = !group || warp == table_of;
       if (CUT && makes_table) {
         // Cut table: start from the scene's seed cut and open the subtree nearest the tile, again and again, until the table
         // is full or only leaves are left. Near the tile the entries end up as single runs (tested directly, like the
@@ -1085,22 +1097,22 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
           wl->span[k][lane] = span[k];
         }
       }
-      if (TABLE && group) {  // warp 0 made the table: hand the slots' intervals (and the slot count) to the other seven
-        if (warp == 0) {
+      if (TABLE && group) {  // the group's first warp made the table: hand the slots' intervals (and the slot count) to the others
+        if (makes_table) {
 #pragma unroll
           for (int k = 0; k < W; ++k) {
-            gs->first[lane + 32 * k] = first[k];
-            gs->span[lane + 32 * k] = span[k];
+            gt->first[lane + 32 * k] = first[k];
+            gt->span[lane + 32 * k] = span[k];
           }
-          if (lane == 0) gs->n_slots = n_slots;
+          if (lane == 0) gt->n_slots = n_slots;
         }
-        __syncthreads();
+        group_sync();
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-          first[k] = gs->first[lane + 32 * k];
-          span[k] = gs->span[lane + 32 * k];
+          first[k] = gt->first[lane + 32 * k];
+          span[k] = gt->span[lane + 32 * k];
         }
-        n_slots = gs->n_slots;
+        n_slots = gt->n_slots;
       }
       int last_slot = -1;       // the slot this lane's previous ray hit
       uint32_t queued = 0;      // deferred rays waiting in wl->ring
@@ -1304,21 +1316,21 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
     }
     bool finish = true;
     if (group) {
-      // the tile's eight units end together: partial sums meet in shared memory and warp 0 adds them in unit order — the
-      // order of the path below, so a pixel's bits do not depend on which of the two ran
-      gs->part_rgbw[q][lane] = make_float4(cr, cg, cb, weight_total);
-      gs->part_blur[q][lane] = blur;
-      __syncthreads();
-      finish = warp == 0;
+      // the tile's units end together: partial sums meet in shared memory and the group's first warp adds them in unit
+      // order — the order of the path below, so a pixel's bits do not depend on which of the two ran
+      gs->part_rgbw[warp][lane] = make_float4(cr, cg, cb, weight_total);
+      gs->part_blur[warp][lane] = blur;
+      group_sync();
+      finish = warp == table_of;
       if (finish) {
-        const float4 p0 = gs->part_rgbw[0][lane];
+        const float4 p0 = gs->part_rgbw[table_of][lane];
         cr = p0.x; cg = p0.y; cb = p0.z; weight_total = p0.w;
-        blur = gs->part_blur[0][lane];
+        blur = gs->part_blur[table_of][lane];
 #pragma unroll 1
         for (uint32_t k = 1; k < a.split; ++k) {
-          const float4 pk = gs->part_rgbw[k][lane];
+          const float4 pk = gs->part_rgbw[table_of + k][lane];
           cr += pk.x; cg += pk.y; cb += pk.z; weight_total += pk.w;
-          blur += gs->part_blur[k][lane];
+          blur += gs->part_blur[table_of + k][lane];
         }
       }
     } else if (a.split > 1) {
@@ -1418,7 +1430,8 @@ __global__ void __launch_bounds__(kBlock, RDC_MIN_BLOCKS) k_render(const RenderA
 // Everything about a launch that follows from the scene and the frame parameters alone.
 struct LaunchPlan {
   int n_iter = 0;
-  bool smem = false, portals = false, table = false, local = false, cut = false, group = false;
+  bool smem = false, portals = false, table = false, local = false, cut = false;
+  uint32_t group = 0;  // warps per group in group mode (= split), 0 = off
   float local_r0 = 0.0f;
   size_t dyn = 0;
   int variant = 0;
@@ -1541,8 +1554,8 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
   while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * L.local_pixels * 20ull > (2ull << 30))) split >>= 1;
   L.split = split;
-  // eight units per tile on a table launch: the eight warps of a block take them together (one table per tile, sums in shared memory)
-  L.group = (L.table || L.cut) && split == (uint32_t)(kBlock / 32);
+  // several units per tile on a table launch: that many warps of a block take them together (one table per tile, sums in shared memory)
+  L.group = ((L.table || L.cut) && split > 1) ? split : 0u;
   if (L.group) L.dyn += sizeof(GroupShared);
   return L;
 }
@@ -1731,7 +1744,7 @@ int render(rdc_scene* s, const rdc_frame_params& p, float4* image, float* blur_m
   const int variant = L.variant;
   const size_t dyn = L.dyn;
   a.split = L.split;
-  a.group = L.group ? 1 : 0;
+  a.group = (int)L.group;
   {
     // the scene's centre in pixels of the full frame (inverse of DeviceCode.cu:103-107), then in tiles of this launch
     const float4 rb = s->dev.root_box;
