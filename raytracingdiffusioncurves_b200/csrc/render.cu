@@ -1535,8 +1535,9 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   // half of it, 4 for a quarter or less. So: the smallest count that gives this LAUNCH at least 12 units per resident warp
   // when the whole scene sits in the run table; at least 48 on the tree and the local run table, whose units trace most of
   // their rays and last several times longer (lady_bug.xml 1080p on the tree: 7.70 ms at 4 units per tile, 9.47 ms at 1);
-  // and only 3 on the cut table, whose units each refine the cut around their tile before the first ray (lady_bug.xml 1080p:
-  // 5.16 ms at 1 unit per tile, 6.92 at 4 — profiles/r02k/units.log).
+  // and 6.5 on the cut table, whose tiles each refine the cut first (lady_bug.xml 1080p: 5.10 ms at 1 unit per tile, 5.51 at 4;
+  // a rank of 4: 1.43 ms at 2, 1.56 at 1; a rank of 8: 0.76 ms at 4, 0.83 at 8 — profiles/r02o/group.log). With more than one
+  // unit per tile a table launch runs in group mode (below), so the units of a tile share its table.
   // The count is part of a pixel's summation order: launches that must agree bit for bit (a frame rendered whole and in
   // parts) pin rdc_frame_params::units_per_tile; hit indices never depend on it.
   const uint32_t tiles_x = (p.image_width + kWarpTileW - 1) / kWarpTileW;
@@ -1544,12 +1545,9 @@ LaunchPlan plan_launch(const rdc_scene* s, const rdc_frame_params& p) {
   L.local_tiles = tiles_x * ((L.local_rows + L.row_skew + kWarpTileH - 1) / kWarpTileH);
   const uint64_t warps = (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) * RDC_MIN_BLOCKS * (kBlock / 32);
   uint32_t split = 1;
-  const uint64_t units_per_warp = L.table ? 12ull : L.cut ? 3ull : 48ull;
-  while (split < (uint32_t)kAutoSplit && (uint64_t)L.local_tiles * split < units_per_warp * warps) split <<= 1;
-  // cut table, launch too small for one tile per warp: go straight to eight units per tile, where a block's eight warps
-  // share the tile's refined cut (group mode) — a rank of 8 on lady_bug.xml 1080p: 0.84 ms against 0.92 at 2 units per tile
-  // and 0.99 at 4 (profiles/r02m/group.log)
-  if (L.cut && split > 1) split = (uint32_t)kAutoSplit;
+  // (in half units per warp) whole-scene table 12, cut table 6.5, tree and local table 48
+  const uint64_t half_units_per_warp = L.table ? 24ull : L.cut ? 13ull : 96ull;
+  while (split < (uint32_t)kAutoSplit && 2ull * L.local_tiles * split < half_units_per_warp * warps) split <<= 1;
   if (p.units_per_tile) split = p.units_per_tile;
   // (a local table is built per unit: it wants at least 64 rays per lane to pay for itself)
   while (split > 1 && ((uint32_t)L.n_iter < (L.local ? 64u : 16u) * split || (uint64_t)split * L.local_pixels * 20ull > (2ull << 30))) split >>= 1;
