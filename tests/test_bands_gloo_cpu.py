@@ -142,8 +142,9 @@ def test_oracle_strips_equal_rows_of_the_full_frame():
 # ---- the peer-memory form (distributed.render_frame_peer) with shared host memory standing in for NVLink peer memory ----
 
 class SharedPeerBuffers:
-    """What distributed.PeerFrameBuffers is on GPUs: every rank can store into every rank's frame buffers. Here the
-    buffers are shared-memory CPU tensors and an 'address' is the tensor itself."""
+    """What rdc_peer_frames (csrc/peer.cu) is on GPUs: every rank can store into every rank's frame buffers. Here the
+    buffers are shared-memory CPU tensors and an 'address' is the tensor itself; render_frame_peer is the Python statement of
+    the sequence rdc_peer_render_frame enqueues (which buffer, which barrier, in which order)."""
 
     def __init__(self, plan, images, sigmas, frames):
         self.plan = plan
