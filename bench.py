@@ -242,15 +242,21 @@ def run_reference(args):
 
 
 def source_sha16():
-    """Hash of the sources the shipped library is built from; profiles/*_ncu.json records the one it was captured with."""
+    """Hash of the CODE the shipped library is built from (comments and white space stripped: editing a comment does not make a
+    profile stale); profiles/r02_ncu_k_render.json records the one its captures were taken with."""
     import hashlib
+    import re
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "raytracingdiffusioncurves_b200", "csrc")
-    for f in sorted(os.listdir(csrc)) + ["../../include/rdc_b200.h", "../../Makefile"]:
+    for f in sorted(os.listdir(csrc)) + ["../../include/rdc_b200.h", "../../include/params.h", "../../Makefile"]:
         path = os.path.join(csrc, f)
         if os.path.isfile(path) and f.endswith((".cu", ".cpp", ".h", "Makefile")):
-            h.update(open(path, "rb").read())
+            text = open(path, "r", errors="replace").read()
+            if not f.endswith("Makefile"):
+                text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)       # block comments
+                text = re.sub(r"(?m)(?<![:\"'])//[^\n]*$", " ", text)    # line comments (not the // of a URL or inside a string start)
+            h.update(" ".join(text.split()).encode())
     return h.hexdigest()[:16]
 
 

@@ -103,8 +103,9 @@ typedef struct rdc_scene_info {
 } rdc_scene_info;
 
 void rdc_default_accel_options(rdc_accel_options* opts);
-/* Uploads the arrays and builds chords + Morton LBVH on `stream`. Synchronises the stream once before
- * returning (the build reads back the chord count), like the reference's set-up phase. */
+/* Uploads the arrays and builds chords, leaf runs and the tree over them (rdc_accel_options::tree) on `stream`.
+ * Synchronises the stream before returning (the build reads back counts; the surface-area tree is built on the
+ * host), like the reference's set-up phase. */
 int rdc_accel_build(const rdc_scene_arrays* arrays, const rdc_accel_options* opts, rdc_stream stream, rdc_scene** out);
 int rdc_scene_get_info(const rdc_scene* scene, rdc_scene_info* out);
 /* Test hook: copies the chord list (original order) to host arrays of n_chords entries each.
@@ -119,12 +120,13 @@ void rdc_scene_destroy(rdc_scene* scene);
 #define RDC_TRAVERSAL_LBVH 0
 #define RDC_TRAVERSAL_BRUTE_FORCE 1 /* every ray against every chord; validates the LBVH at full size */
 /* how primary rays find their closest chord (rdc_frame_params::route); every route gives the same bits */
-#define RDC_ROUTE_AUTO 0        /* whole-scene run table up to 64 runs, per-tile local run table for large scenes
-                                   seen closely enough, the cut table for the scenes in between               */
-#define RDC_ROUTE_TREE 1        /* always the LBVH                                                            */
+#define RDC_ROUTE_AUTO 0        /* whole-scene run table up to 64 runs; per-tile cut table for every larger scene that
+                                   has a surface-area tree (up to 65 536 runs); per-tile local run table beyond,
+                                   when the view is close enough; the tree otherwise                           */
+#define RDC_ROUTE_TREE 1        /* always the tree                                                            */
 #define RDC_ROUTE_LOCAL_TABLE 2 /* per-tile local run table whatever the size of the scene                     */
-#define RDC_ROUTE_CUT_TABLE 3   /* per-tile table over a 64-entry cut through the tree (scenes of more than 64 runs
-                                   that have a surface-area tree)                                              */
+#define RDC_ROUTE_CUT_TABLE 3   /* per-tile table over a cut through the tree, refined around every tile (scenes of
+                                   more than 64 runs that have a surface-area tree)                            */
 
 typedef struct rdc_frame_params {
   uint32_t image_width, image_height;   /* output size (params.h:48-49)                               */
