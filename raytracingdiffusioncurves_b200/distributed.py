@@ -1,8 +1,8 @@
 """Partitioning of one frame over the GPUs of a box.
 
 One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests). The curve set and its tree are
-replicated. Random numbers are keyed by the GLOBAL pixel index, so the assembled frame is bit-identical to
-the single-GPU frame whatever the split.
+replicated. Random numbers are keyed by the GLOBAL pixel index, so the assembled frame has the single-GPU frame's hits
+whatever the split — and its pixels bit for bit when rdc_frame_params::units_per_tile is pinned.
 
 Rendering is dealt out in STRIPS of 8 rows, round-robin: rank r renders strips t with t % world == r. A
 contiguous band per rank (the obvious split) is badly balanced on sparse scenes — in arch.xml the rows that
