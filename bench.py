@@ -508,6 +508,8 @@ def roofline_block(work, k, fp32_peak, l2_peak, hbm_peak, single_gpu):
     return {
         "bound": "fp32", "kernel": "k_render", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": cap.get("dram_bytes") if cap else None,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch under ncu --set full (profiles/r02_ncu_k_render.json); "
+                        "below the algorithmic bytes where the frame the launch writes is still in the 126 MB L2 when it ends",
         "issue_slots": cap,
         "peak_source": "dependent-FFMA microbenchmark (rdc_microbench_fp32) run in this process; MEASURED_PEAKS.json has no FP32 figure",
         "kernel_ms": k["kernel_ms"], "flops_per_ray": k["flops_per_ray"], "per_ray": k["per_ray"],
